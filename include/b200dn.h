@@ -1,0 +1,169 @@
+/*
+ * b200dn.h — C ABI of the B200-native RDUNet denoising hot path (libb200dn.so).
+ *
+ * Every entry point enqueues work on the caller's CUDA stream (`stream` is a
+ * cudaStream_t passed as void*), performs no hidden synchronisation, never
+ * throws across the ABI, and returns 0 on success or a negative B200DN_E_* code
+ * (text via b200dn_last_error()).  All pointers are raw device pointers unless
+ * the name says "host".  There is no CPU fallback: on a machine without an
+ * sm_100 GPU every compute call returns B200DN_E_CUDA.
+ *
+ * What each entry point replaces in the reference (pierregab/VUB_Image_denoising,
+ * paths relative to the reference root):
+ *
+ *   b200dn_igemm            nn.Conv2d(.,.,3,padding=1)+nn.PReLU      UNet/RDUNet_model.py:61,74-75,86-87,98-101
+ *                           torch.cat in the dense block (eliminated) UNet/RDUNet_model.py:107-115
+ *                           `out_3 + x` dense residual               UNet/RDUNet_model.py:115
+ *                           nn.Conv2d(C,2C,2,stride=2)+PReLU         UNet/RDUNet_model.py:49-56
+ *                           nn.ConvTranspose2d(C,C,2,stride=2)+PReLU UNet/RDUNet_model.py:62,66-68
+ *                           OutputBlock.conv_2 + `+ inputs`          UNet/RDUNet_model.py:83-93,186
+ *   b200dn_conv_in          InputBlock.conv_1 + actv_1, t-plane cat  UNet/RDUNet_model.py:71-81,
+ *                                                                    diffusion_denoising/Unet/Unet_model.py:133-136
+ *   b200dn_pack_conv_weight / b200dn_pack_convt_weight
+ *                           state_dict layout -> kernel layout       (OIHW / IOHW fp32 -> [plane][tap][CoutPad][CinPad])
+ *   b200dn_sampler_step     x_t - x_tilde + x_tilde_prev             diffusion_denoising/diffusion_RDUnet.py:45,48,49
+ *   b200dn_lerp             forward_diffusion                        diffusion_denoising/diffusion_RDUnet.py:33-36
+ *   b200dn_psnr_sse         calculate_psnr / peak_signal_noise_ratio evaluate_Unet_diffusion/evaluate_model.py:36-41,
+ *                                                                    evaluate_SIDD/evaluate_SIDD.py:63
+ *   b200dn_ssim             skimage structural_similarity call sites evaluate_Unet_diffusion/evaluate_model.py:30-34,
+ *                                                                    evaluate_SIDD/evaluate_SIDD.py:64
+ *   b200dn_gauss_noise_u8   np.random.normal + clip + uint8 + ToTensor/Normalize
+ *                                                                    dataset_creation/custom_dataset.py:83-87,
+ *                                                                    dataset_creation/data_loader.py:35-38
+ *   b200dn_u8_to_norm       ToTensor + Normalize(0.5, 0.5)           evaluate_SIDD/evaluate_SIDD.py:23-26,
+ *                                                                    evaluate_SIDD/benchmark.py:35-36
+ *   b200dn_norm_to_u8       (y+1)/2 -> clip(.*255) -> uint8          evaluate_SIDD/benchmark.py:42-44
+ */
+#ifndef B200DN_H_
+#define B200DN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DN_ABI_VERSION 1
+
+/* error codes */
+#define B200DN_OK          0
+#define B200DN_E_ARG      -1   /* bad argument (shape, alignment, enum)           */
+#define B200DN_E_CUDA     -2   /* CUDA runtime / driver error, no sm_100 device   */
+#define B200DN_E_UNSUP    -3   /* valid request the kernels do not support        */
+
+/* storage / MMA precision of the 16-bit activation path */
+#define B200DN_PREC_BF16     0  /* bf16 weights x bf16 activations, 1 MMA          */
+#define B200DN_PREC_FP16     1  /* fp16 weights x fp16 activations, 1 MMA          */
+#define B200DN_PREC_BF16X2   2  /* bf16 W x (bf16 hi + bf16 lo) activations, 2 MMA */
+#define B200DN_PREC_BF16X3   3  /* (W hi+lo) x (A hi+lo) minus lo*lo, 3 MMA: fp32 validation build */
+
+/* implicit-GEMM modes */
+#define B200DN_MODE_CONV3X3  0  /* 3x3, stride 1, zero pad 1 (taps = 9)            */
+#define B200DN_MODE_DOWN2X2  1  /* 2x2, stride 2 (taps = 4)                        */
+#define B200DN_MODE_UP2X2    2  /* transposed 2x2, stride 2 (4 N-groups)           */
+#define B200DN_MODE_CONV1X1  3  /* 1 tap, no shift (used by tests / microbenchmarks)*/
+
+/* epilogue output kinds */
+#define B200DN_OUT_NHWC16    0  /* 16-bit NHWC planes into a channel slice         */
+#define B200DN_OUT_NCHW32    1  /* fp32 NCHW (+ fp32 NCHW residual), module boundary */
+
+const char* b200dn_last_error(void);
+int b200dn_abi_version(void);
+/* number of SMs of the current device, or <0 */
+int b200dn_sm_count(void);
+
+/* ---- weight packing --------------------------------------------------------
+ * Output layout (16-bit elements): [n_wplanes][groups][cout_pad][cin_pad], K(cin)-contiguous,
+ * zero padded; cin_pad = roundup(Cin,64), cout_pad = roundup(Cout,16).
+ * groups = kh*kw taps (conv) or 4 output phases ky*2+kx (convT).
+ * n_wplanes = 2 only for B200DN_PREC_BF16X3 (hi, lo), else 1.
+ * Conv2d weight is OIHW [Cout,Cin,kh,kw]; ConvTranspose2d weight is IOHW [Cin,Cout,2,2].
+ */
+int b200dn_pack_conv_weight(const float* w_oihw, int cout, int cin, int kh, int kw,
+                            int prec, void* packed, void* stream);
+int b200dn_pack_convt_weight(const float* w_iohw, int cin, int cout,
+                             int prec, void* packed, void* stream);
+/* bytes needed for a packed weight */
+int64_t b200dn_packed_weight_bytes(int cout, int cin, int groups, int prec);
+
+/* ---- the tensor-core implicit GEMM ---------------------------------------- */
+typedef struct b200dn_igemm_args {
+  int32_t mode;            /* B200DN_MODE_*                                          */
+  int32_t prec;            /* B200DN_PREC_*                                          */
+  int32_t B, H, W;         /* INPUT batch and spatial size (NHWC)                    */
+  int32_t cin, cout;       /* logical channels (cout per phase for UP2X2)            */
+  /* input activation planes: NHWC, `in_ctot` channels per pixel, the conv reads
+     channels [0, cin).  in[1] is the bf16 "lo" plane (BF16X2/X3), else NULL.        */
+  const void* in[2];
+  int32_t in_ctot;
+  const void* wpacked;     /* from b200dn_pack_*                                     */
+  const float* bias;       /* [cout] fp32                                            */
+  const float* slope;      /* [cout] fp32 PReLU slopes, NULL = no activation         */
+  int32_t out_kind;        /* B200DN_OUT_*                                           */
+  /* OUT_NHWC16: writes channels [out_coff, out_coff+cout) of out[] (out_ctot per pixel);
+     output spatial size is HxW (CONV), H/2xW/2 (DOWN), 2Hx2W (UP).                  */
+  void* out[2];
+  int32_t out_ctot, out_coff;
+  /* optional NHWC residual added after PReLU (dense-block `+ x`): channels [0,cout) */
+  const void* res[2];
+  int32_t res_ctot;
+  /* OUT_NCHW32: out_nchw[B,cout,H,W] = prelu(conv) + res_nchw[b % res_bmod]        */
+  float* out_nchw;
+  const float* res_nchw;
+  int32_t res_bmod;
+  int32_t block_n;         /* 0 = auto; else UMMA N (multiple of 16, <= 256)         */
+  int32_t max_ctas;        /* 0 = one per SM                                         */
+} b200dn_igemm_args;
+
+int b200dn_igemm(const b200dn_igemm_args* args, void* stream);
+
+/* ---- input block conv_1 (Cin = 3 or 4), CUDA cores, fp32 math ---------------
+ * x: fp32 NCHW [Bx,3,H,W]; image b of the output reads x[b % Bx].
+ * t: optional timestep plane source; element (b,y,x) = t[b*t_sb + y*t_sh + x*t_sw]
+ *    (strides in elements, 0 = broadcast).  NULL -> 3-channel network.
+ * w: OIHW fp32 [cout, 3|4, 3, 3].  Output: NHWC 16-bit planes, channels [0,cout).
+ */
+int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_sb, int64_t t_sh, int64_t t_sw,
+                   int B, int H, int W, int cout,
+                   const float* w, const float* bias, const float* slope,
+                   int prec, void* out0, void* out1, int out_ctot, void* stream);
+
+/* ---- sampler elementwise ---------------------------------------------------- */
+/* x_next = (x - ((1-a_t)*u1 + a_t*y)) + ((1-a_p)*u2 + a_p*y), fp32, reference op order.
+   one_m_at etc. are the fp32-rounded python scalars.  n = element count.            */
+int b200dn_sampler_step(const float* x, const float* u1, const float* u2, const float* y,
+                        float one_m_at, float at, float one_m_ap, float ap,
+                        float* x_next, int64_t n, void* stream);
+/* out = alpha*noisy + (1-alpha)*clean */
+int b200dn_lerp(const float* clean, const float* noisy, float alpha, float one_m_alpha,
+                float* out, int64_t n, void* stream);
+
+/* ---- metrics ------------------------------------------------------------------ */
+/* sse[i] (fp64) = sum over the n_per_image elements of image i of (a-b)^2            */
+int b200dn_psnr_sse(const float* a, const float* b, int64_t n_images, int64_t n_per_image,
+                    double* sse, void* stream);
+/* skimage-0.22-style SSIM (7x7 uniform window, sample covariance, crop 3, K1=.01 K2=.03)
+   on fp32 planes: a,b are [n_planes,H,W]; ssim_sum[p] (fp64) = sum of S over the cropped
+   interior of plane p (divide by (H-6)*(W-6) for the mean).                           */
+int b200dn_ssim(const float* a, const float* b, int64_t n_planes, int H, int W,
+                float data_range, double* ssim_sum, void* stream);
+
+/* ---- noise synthesis / data formats ------------------------------------------- */
+/* clean_u8: [B,H,W,C] uint8 (HWC as in PIL / the SIDD .mat blocks).
+   noisy_u8 (optional, same layout), noisy_norm (optional) fp32 NCHW in [-1,1],
+   clean_norm (optional) fp32 NCHW.  sigma[b] per image.  Philox4x32-10,
+   key=(seed_lo,seed_hi), counter=(elem_idx/4 lo, hi, stream_id, 0), Box-Muller.     */
+int b200dn_gauss_noise_u8(const uint8_t* clean_u8, int B, int H, int W, int C,
+                          const float* sigma, uint64_t seed, uint32_t stream_id,
+                          uint8_t* noisy_u8, float* noisy_norm, float* clean_norm, void* stream);
+/* raw fp32 standard normals z[i], same generator (for pinning the RNG itself)        */
+int b200dn_philox_normal(float* z, int64_t n, uint64_t seed, uint32_t stream_id, void* stream);
+/* u8 HWC [B,H,W,C] -> fp32 NCHW (x/255 - 0.5)/0.5 */
+int b200dn_u8_to_norm(const uint8_t* in, int B, int H, int W, int C, float* out, void* stream);
+/* fp32 NCHW in [-1,1] -> u8 HWC: trunc(clip((y+1)/2*255, 0, 255)) */
+int b200dn_norm_to_u8(const float* in, int B, int H, int W, int C, uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DN_H_ */

@@ -1,0 +1,83 @@
+"""Shared helpers of the parity tests (layout conversion between the reference's NCHW fp32 world and the
+kernels' NHWC 16-bit planes, digests, tolerances)."""
+from __future__ import annotations
+
+import hashlib
+
+import torch
+
+from vub_image_denoising_b200 import _lib
+
+PIX_TOL = 2.0 / 255.0          # 1/255 in [0,1] space == 2/255 in the networks' [-1,1] space
+
+
+def sd_digest(sd) -> str:
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(str(tuple(v.shape)).encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def dt16(prec: int):
+    return torch.float16 if prec == _lib.PREC_FP16 else torch.bfloat16
+
+
+def two_planes(prec: int) -> bool:
+    return prec in (_lib.PREC_BF16X2, _lib.PREC_BF16X3)
+
+
+def to_planes(x_nchw: torch.Tensor, prec: int, ctot: int | None = None, coff: int = 0):
+    """fp32 NCHW -> (hi, lo|None) NHWC int16-storage planes with `ctot` channels (x placed at [coff, coff+C))."""
+    B, Cn, H, W = x_nchw.shape
+    ctot = ctot or Cn
+    d = dt16(prec)
+    nhwc = x_nchw.permute(0, 2, 3, 1).contiguous()
+    hi = nhwc.to(d)
+    full_hi = torch.zeros((B, H, W, ctot), dtype=d, device=x_nchw.device)
+    full_hi[..., coff:coff + Cn] = hi
+    lo_t = None
+    if two_planes(prec):
+        lo = (nhwc - hi.float()).to(d)
+        lo_t = torch.zeros((B, H, W, ctot), dtype=d, device=x_nchw.device)
+        lo_t[..., coff:coff + Cn] = lo
+        lo_t = lo_t.view(torch.int16)
+    return full_hi.view(torch.int16), lo_t
+
+
+def from_planes(hi: torch.Tensor, lo, prec: int, coff: int, c: int) -> torch.Tensor:
+    """(hi, lo) NHWC planes -> fp32 NCHW of channels [coff, coff+c)."""
+    d = dt16(prec)
+    v = hi.view(d)[..., coff:coff + c].float()
+    if lo is not None:
+        v = v + lo.view(d)[..., coff:coff + c].float()
+    return v.permute(0, 3, 1, 2).contiguous()
+
+
+def effective_input(x_nchw: torch.Tensor, prec: int) -> torch.Tensor:
+    """The value the kernel actually sees for an fp32 activation under `prec` (hi [+ lo])."""
+    d = dt16(prec)
+    hi = x_nchw.to(d).float()
+    if two_planes(prec):
+        return hi + (x_nchw - hi).to(d).float()
+    return hi
+
+
+def effective_weight(w: torch.Tensor, prec: int) -> torch.Tensor:
+    d = dt16(prec)
+    hi = w.to(d).float()
+    if prec == _lib.PREC_BF16X3:
+        return hi + (w - hi).to(d).float()
+    return hi
+
+
+def out_tol(ref: torch.Tensor, prec: int) -> torch.Tensor:
+    """Per-element tolerance for a 16-bit stored output: 1 ulp of the storage format + fp32 accumulation slack."""
+    if two_planes(prec):
+        rel = 2.0 ** -15
+    elif prec == _lib.PREC_FP16:
+        rel = 2.0 ** -10
+    else:
+        rel = 2.0 ** -7
+    return ref.abs() * rel + (1e-4 if two_planes(prec) else 2e-3)

@@ -1,0 +1,212 @@
+"""GPU parity of every fused layer kernel, called through the C ABI (torch.ops.b200dn.* -> libb200dn.so),
+against the oracle's arithmetic (plain fp64 conv / PReLU / add on the operands the kernel actually sees).
+
+Reference semantics checked: Conv2d(3x3, pad 1)+PReLU with dense-block slice writes and `+ x` residual
+(UNet/RDUNet_model.py:95-115), Conv2d(2x2, stride 2)+PReLU (:49-56), ConvTranspose2d(2x2, stride 2)+PReLU
+scattered into the cat buffer (:58-69), OutputBlock.conv_2 + `+ inputs` (:83-93,186), InputBlock.conv_1 with
+the RDUNet_T timestep plane (diffusion_denoising/Unet/Unet_model.py:133-136).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import effective_input, effective_weight, from_planes, out_tol, to_planes, two_planes, dt16
+from vub_image_denoising_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+PRECS = [_lib.PREC_BF16, _lib.PREC_FP16, _lib.PREC_BF16X2, _lib.PREC_BF16X3]
+PREC_IDS = ["bf16", "fp16", "bf16x2", "bf16x3"]
+
+
+def _rand(*shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def _mk_out(B, H, W, ctot, prec):
+    d = dt16(prec)
+    hi = torch.full((B, H, W, ctot), 7.0, dtype=d, device=DEV).view(torch.int16)
+    lo = torch.full((B, H, W, ctot), 7.0, dtype=d, device=DEV).view(torch.int16) if two_planes(prec) else None
+    return hi, lo
+
+
+def _check_slice(hi, lo, prec, coff, cout, ref, what):
+    got = from_planes(hi, lo, prec, coff, cout)
+    err = (got.double().cpu() - ref).abs()
+    tol = out_tol(ref, prec)
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} / {bad.numel()} outside tolerance, max err {float(err.max()):.3e}"
+    # everything outside the slice must be untouched (the kernels write channel slices of shared buffers)
+    d = dt16(prec)
+    full = hi.view(d).float()
+    mask = torch.ones(full.shape[-1], dtype=torch.bool, device=full.device)
+    mask[coff:coff + cout] = False
+    assert torch.all(full[..., mask] == 7.0), f"{what}: wrote outside its channel slice"
+
+
+CONV_CASES = [
+    # B, H, W, cin, cout, extra_in, ctot_out, coff, residual
+    (1, 8, 16, 16, 16, 0, 16, 0, False),        # one full tile, one k16 step per tap
+    (2, 24, 40, 80, 16, 16, 96, 80, False),     # dense-block growth slice, partial K block, partial tiles
+    (1, 16, 16, 64, 64, 0, 64, 0, True),        # residual
+    (1, 32, 32, 160, 64, 0, 160, 96, False),    # 3 K blocks (last partial)
+    (1, 16, 32, 128, 256, 0, 256, 0, False),    # N = 256
+    (1, 16, 16, 64, 512, 0, 512, 0, True),      # two N tiles + residual
+    (1, 8, 8, 24, 8, 16, 40, 24, False),        # base_filters 16 level 0: cin 24, cout 8 (N padded to 16)
+    (3, 40, 24, 48, 48, 0, 48, 0, True),        # N = 48
+]
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
+@pytest.mark.parametrize("case", CONV_CASES, ids=[f"c{i}" for i in range(len(CONV_CASES))])
+def test_conv3x3_bias_prelu(case, prec, built_lib):
+    B, H, W, cin, cout, extra, ctot_out, coff, residual = case
+    x = _rand(B, cin, H, W, seed=1)
+    w = _rand(cout, cin, 3, 3, seed=2, scale=(2.0 / (9 * cin)) ** 0.5)
+    bias = _rand(cout, seed=3, scale=0.1)
+    slope = torch.rand(cout, device=DEV) * 0.5
+    x_hi, x_lo = to_planes(x, prec, ctot=cin + extra)
+    if extra:  # poison the channels the conv must not read
+        x_hi.view(dt16(prec))[..., cin:] = 1000.0
+    wp = torch.ops.b200dn.pack_weight(w, prec, False)
+    out_hi, out_lo = _mk_out(B, H, W, ctot_out, prec)
+    res = _rand(B, cout, H, W, seed=4) if residual else None
+    r_hi, r_lo = to_planes(res, prec) if residual else (None, None)
+    torch.ops.b200dn.conv_igemm(x_hi, x_lo, wp, bias, slope, _lib.MODE_CONV3X3, prec, cin, cout,
+                                out_hi, out_lo, coff, r_hi, r_lo)
+    torch.cuda.synchronize()
+    ref = F.conv2d(effective_input(x, prec).double().cpu(), effective_weight(w, prec).double().cpu(),
+                   bias.double().cpu(), padding=1)
+    ref = F.prelu(ref, slope.double().cpu())
+    if residual:
+        ref = ref + effective_input(res, prec).double().cpu()
+    _check_slice(out_hi, out_lo, prec, coff, cout, ref, "conv3x3")
+
+
+@pytest.mark.parametrize("block_n,max_ctas", [(16, 0), (32, 3), (64, 1), (128, 0)])
+def test_conv3x3_tilings_agree(block_n, max_ctas, built_lib):
+    """Different N tilings / CTA counts (multi-tile persistence, TMEM double buffering) give the same bits."""
+    prec = _lib.PREC_BF16
+    B, H, W, cin, cout = 2, 32, 48, 96, 128
+    x = _rand(B, cin, H, W, seed=5)
+    w = _rand(cout, cin, 3, 3, seed=6, scale=0.05)
+    bias = _rand(cout, seed=7, scale=0.1)
+    slope = torch.full((cout,), 0.25, device=DEV)
+    x_hi, _ = to_planes(x, prec)
+    wp = torch.ops.b200dn.pack_weight(w, prec, False)
+    base_hi, _ = _mk_out(B, H, W, cout, prec)
+    torch.ops.b200dn.conv_igemm(x_hi, None, wp, bias, slope, _lib.MODE_CONV3X3, prec, cin, cout, base_hi, None, 0,
+                                None, None)
+    out_hi, _ = _mk_out(B, H, W, cout, prec)
+    torch.ops.b200dn.conv_igemm(x_hi, None, wp, bias, slope, _lib.MODE_CONV3X3, prec, cin, cout, out_hi, None, 0,
+                                None, None, block_n, max_ctas)
+    torch.cuda.synchronize()
+    assert torch.equal(base_hi, out_hi)
+
+
+DOWN_CASES = [(1, 16, 32, 16, 32), (2, 24, 40, 64, 128), (1, 64, 64, 128, 256), (1, 8, 8, 32, 64)]
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
+@pytest.mark.parametrize("case", DOWN_CASES, ids=[f"d{i}" for i in range(len(DOWN_CASES))])
+def test_down2x2(case, prec, built_lib):
+    B, H, W, cin, cout = case
+    x = _rand(B, cin, H, W, seed=11)
+    w = _rand(cout, cin, 2, 2, seed=12, scale=(2.0 / (4 * cin)) ** 0.5)
+    bias = _rand(cout, seed=13, scale=0.1)
+    slope = torch.rand(cout, device=DEV) * 0.5
+    x_hi, x_lo = to_planes(x, prec, ctot=cin * 3)          # reads the skip slice of a 3C cat buffer
+    wp = torch.ops.b200dn.pack_weight(w, prec, False)
+    ctot_out = cout * 5 // 2
+    out_hi, out_lo = _mk_out(B, H // 2, W // 2, ctot_out, prec)
+    torch.ops.b200dn.conv_igemm(x_hi, x_lo, wp, bias, slope, _lib.MODE_DOWN2X2, prec, cin, cout,
+                                out_hi, out_lo, 0, None, None)
+    torch.cuda.synchronize()
+    ref = F.conv2d(effective_input(x, prec).double().cpu(), effective_weight(w, prec).double().cpu(),
+                   bias.double().cpu(), stride=2)
+    ref = F.prelu(ref, slope.double().cpu())
+    _check_slice(out_hi, out_lo, prec, 0, cout, ref, "down2x2")
+
+
+UP_CASES = [(1, 8, 16, 32), (2, 12, 20, 64), (1, 32, 32, 256), (1, 4, 4, 128)]
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
+@pytest.mark.parametrize("case", UP_CASES, ids=[f"u{i}" for i in range(len(UP_CASES))])
+def test_up2x2_scatter(case, prec, built_lib):
+    B, H, W, c = case                      # ConvTranspose2d(c, c, 2, stride=2)
+    x = _rand(B, c, H, W, seed=21)
+    w = _rand(c, c, 2, 2, seed=22, scale=(1.0 / c) ** 0.5)   # IOHW
+    bias = _rand(c, seed=23, scale=0.1)
+    slope = torch.rand(c, device=DEV) * 0.5
+    x_hi, x_lo = to_planes(x, prec, ctot=c * 5 // 2)
+    wp = torch.ops.b200dn.pack_weight(w, prec, True)
+    cskip = c // 2
+    ctot_out = cskip + c                   # [skip | upsampled]
+    out_hi, out_lo = _mk_out(B, 2 * H, 2 * W, ctot_out, prec)
+    torch.ops.b200dn.conv_igemm(x_hi, x_lo, wp, bias, slope, _lib.MODE_UP2X2, prec, c, c,
+                                out_hi, out_lo, cskip, None, None)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(effective_input(x, prec).double().cpu(), effective_weight(w, prec).double().cpu(),
+                             bias.double().cpu(), stride=2)
+    ref = F.prelu(ref, slope.double().cpu())
+    _check_slice(out_hi, out_lo, prec, cskip, c, ref, "up2x2")
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
+@pytest.mark.parametrize("B,bx,H,W,cin", [(1, 1, 16, 16, 16), (4, 2, 24, 40, 32), (2, 2, 8, 8, 128)])
+def test_output_conv_nchw_residual(B, bx, H, W, cin, prec, built_lib):
+    x = _rand(B, cin, H, W, seed=31)
+    w = _rand(3, cin, 3, 3, seed=32, scale=(2.0 / (9 * cin)) ** 0.5)
+    bias = _rand(3, seed=33, scale=0.1)
+    slope = torch.rand(3, device=DEV) * 0.5
+    inputs = _rand(bx, 3, H, W, seed=34)
+    x_hi, x_lo = to_planes(x, prec)
+    wp = torch.ops.b200dn.pack_weight(w, prec, False)
+    out = torch.full((B, 3, H, W), 9.0, device=DEV)
+    torch.ops.b200dn.conv_out_nchw(x_hi, x_lo, wp, bias, slope, prec, cin, 3, inputs, out, bx)
+    torch.cuda.synchronize()
+    ref = F.conv2d(effective_input(x, prec).double().cpu(), effective_weight(w, prec).double().cpu(),
+                   bias.double().cpu(), padding=1)
+    ref = F.prelu(ref, slope.double().cpu()) + inputs.double().cpu().repeat(B // bx, 1, 1, 1)
+    err = (out.double().cpu() - ref).abs().max()
+    assert float(err) < 5e-5, f"output conv (fp32 NCHW) max err {float(err):.3e}"
+
+
+@pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
+@pytest.mark.parametrize("with_t", [False, True])
+@pytest.mark.parametrize("B,bx,H,W,cout", [(1, 1, 8, 8, 16), (4, 2, 24, 40, 32), (2, 2, 16, 72, 128)])
+def test_conv_in(B, bx, H, W, cout, with_t, prec, built_lib):
+    cin = 4 if with_t else 3
+    x = _rand(bx, 3, H, W, seed=41)
+    w = _rand(cout, cin, 3, 3, seed=42, scale=(2.0 / (9 * cin)) ** 0.5)
+    bias = _rand(cout, seed=43, scale=0.1)
+    slope = torch.rand(cout, device=DEV) * 0.5
+    t = torch.rand(B, device=DEV) if with_t else None
+    ctot = cout + 16
+    out_hi, out_lo = _mk_out(B, H, W, ctot, prec)
+    torch.ops.b200dn.conv_in(x, t, w, bias, slope, prec, B, out_hi, out_lo)
+    torch.cuda.synchronize()
+    xin = x.double().cpu().repeat(B // bx, 1, 1, 1)
+    if with_t:
+        xin = torch.cat([xin, t.double().cpu().view(B, 1, 1, 1).expand(B, 1, H, W)], 1)
+    ref = F.prelu(F.conv2d(xin, w.double().cpu(), bias.double().cpu(), padding=1), slope.double().cpu())
+    _check_slice(out_hi, out_lo, prec, 0, cout, ref, "conv_in")
+
+
+def test_igemm_argument_errors(built_lib):
+    """Bad arguments come back as RuntimeError carrying the C-side message, as the reference's shape errors do."""
+    prec = _lib.PREC_BF16
+    x_hi = torch.zeros((1, 8, 8, 20), dtype=torch.int16, device=DEV)      # ctot not a multiple of 8
+    out = torch.zeros((1, 8, 8, 16), dtype=torch.int16, device=DEV)
+    w = torch.zeros((16, 16, 3, 3), device=DEV)
+    wp = torch.ops.b200dn.pack_weight(w, prec, False)
+    b = torch.zeros(16, device=DEV)
+    with pytest.raises(RuntimeError, match="in_ctot"):
+        torch.ops.b200dn.conv_igemm(x_hi, None, wp, b, b, _lib.MODE_CONV3X3, prec, 16, 16, out, None, 0, None, None)
+    x_ok = torch.zeros((1, 8, 8, 16), dtype=torch.int16, device=DEV)
+    with pytest.raises(RuntimeError, match="lo activation plane"):
+        torch.ops.b200dn.conv_igemm(x_ok, None, wp, b, b, _lib.MODE_CONV3X3, _lib.PREC_BF16X2, 16, 16, out, None, 0,
+                                    None, None)

@@ -1,0 +1,187 @@
+"""GPU parity of the whole drop-in path against the reference's own outputs (golden vectors produced by
+oracle/pin_against_reference.py from the real reference modules) and against the oracle on fresh inputs.
+
+Bars (BASELINE.json north_star): bf16 path >= 99.9 % of pixels within 1/255 in [0,1] space and PSNR within
+0.02 dB; fp32 validation build (bf16x3) <= 1e-4 max abs error.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import PIX_TOL, sd_digest
+import vub_image_denoising_b200 as b2
+from oracle import rdunet_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _frac_within(a: torch.Tensor, b: torch.Tensor) -> float:
+    return float(((a - b).abs() <= PIX_TOL).double().mean())
+
+
+def _psnr_db(ref: torch.Tensor, x: torch.Tensor, data_range=2.0) -> float:
+    mse = float(((ref.double() - x.double()) ** 2).mean())
+    return 10 * math.log10(data_range ** 2 / mse)
+
+
+def _check_bar(got, ref, clean=None, what=""):
+    frac = _frac_within(got, ref)
+    mx = float((got - ref).abs().max())
+    assert frac >= 0.999, f"{what}: only {frac * 100:.3f}% of pixels within 1/255 (max err {mx:.3e})"
+    if clean is not None:
+        d = abs(_psnr_db(clean, got) - _psnr_db(clean, ref))
+        assert d <= 0.02, f"{what}: PSNR differs by {d:.4f} dB"
+    return frac, mx
+
+
+@pytest.mark.parametrize("precision,max_abs", [("bf16", None), ("fp16", None), ("bf16x2", None), ("bf16x3", 1e-4)])
+def test_rdunet_golden(golden, precision, max_abs, built_lib):
+    torch.manual_seed(7)
+    net = b2.RDUNet(base_filters=16)
+    assert sd_digest(net.state_dict()) == bytes(golden["A_digest"]).hex(), "init differs from the reference ctor"
+    net = net.to(DEV).eval()
+    net.precision = precision
+    with torch.no_grad():
+        for k in ("0", "1"):
+            x = torch.from_numpy(golden[f"A_x{k}"]).to(DEV)
+            ref = torch.from_numpy(golden[f"A_y{k}"]).to(DEV)
+            got = net(x)
+            assert got.shape == ref.shape and got.dtype == torch.float32
+            _check_bar(got, ref, what=f"RDUNet(16) {precision} case {k}")
+            if max_abs is not None:
+                assert float((got - ref).abs().max()) <= max_abs
+
+
+@pytest.mark.parametrize("precision,max_abs", [("bf16", None), ("bf16x2", None), ("bf16x3", 1e-4)])
+def test_rdunet_t_golden(golden, precision, max_abs, built_lib):
+    torch.manual_seed(11)
+    net = b2.RDUNet_T(base_filters=16)
+    assert sd_digest(net.state_dict()) == bytes(golden["B_digest"]).hex()
+    net = net.to(DEV).eval()
+    net.precision = precision
+    x = torch.from_numpy(golden["B_x"]).to(DEV)
+    with torch.no_grad():
+        for k in ("0", "1"):
+            t = torch.from_numpy(golden[f"B_t{k}"]).to(DEV)
+            ref = torch.from_numpy(golden[f"B_y{k}"]).to(DEV)
+            got = net(x, t)
+            _check_bar(got, ref, what=f"RDUNet_T(16) {precision} t{k}")
+            if max_abs is not None:
+                assert float((got - ref).abs().max()) <= max_abs
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+@pytest.mark.parametrize("precision,max_abs", [("bf16x2", None), ("bf16x3", 1e-4)])
+def test_sampler_golden(golden, precision, max_abs, use_graph, built_lib):
+    torch.manual_seed(13)
+    dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=16), timesteps=4)
+    assert sd_digest(dm.state_dict()) == bytes(golden["C_digest"]).hex()
+    dm = dm.to(DEV).eval()
+    dm.precision = precision
+    dm.use_cuda_graph = use_graph
+    noisy = torch.from_numpy(golden["C_noisy"]).to(DEV)
+    clean = torch.from_numpy(golden["C_clean"]).to(DEV)
+    ref = torch.from_numpy(golden["C_out"]).to(DEV)
+    keep = noisy.clone()
+    got = dm.improved_sampling(noisy)
+    assert torch.equal(noisy, keep), "improved_sampling must not write its input"
+    assert got.data_ptr() != noisy.data_ptr()
+    _check_bar(got, ref, what=f"sampler T=4 {precision}")
+    if max_abs is not None:
+        assert float((got - ref).abs().max()) <= max_abs
+    # second call reuses the captured graph / cached plan and must give the same bits
+    again = dm.improved_sampling(noisy)
+    assert torch.equal(got, again)
+    # forward_diffusion is exact fp32 arithmetic
+    fd = dm.forward_diffusion(clean, noisy, 3)
+    assert torch.equal(fd, torch.from_numpy(golden["C_fd3"]).to(DEV))
+    # forward = forward_diffusion + improved_sampling
+    full = dm(clean, noisy, 3)
+    assert torch.equal(full, dm.improved_sampling(fd))
+
+
+def test_eval_width_t32_golden(golden, built_lib):
+    """The reference's evaluation width for the sampler network: RDUNet_T(base_filters=32)."""
+    torch.manual_seed(7)
+    dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=32), timesteps=20)
+    assert sd_digest(dm.state_dict()) == bytes(golden["D_digest_T32"]).hex()
+    dm = dm.to(DEV).eval()
+    x = torch.from_numpy(golden["D_x"]).to(DEV)
+    ref = torch.from_numpy(golden["D_y"]).to(DEV)
+    t = torch.tensor([0.5], device=DEV).view(1, 1, 1, 1)
+    with torch.no_grad():
+        for precision, bound in (("bf16", None), ("bf16x2", None), ("bf16x3", 1e-4)):
+            dm.unet.precision = precision
+            got = dm.unet(x, t)
+            frac, mx = _check_bar(got, ref, what=f"RDUNet_T(32) {precision}")
+            if bound:
+                assert mx <= bound, f"{precision}: max err {mx:.3e}"
+
+
+def test_sampler_full_schedule_vs_oracle(built_lib):
+    """Full 20-step schedule, F=32, against the fp32 CPU oracle on a fresh seeded input (64x64 keeps the oracle
+    to a few seconds).  bf16x2 must hold the 99.9%-within-1/255 bar, bf16x3 the 1e-4 bar."""
+    torch.manual_seed(3)
+    dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=32), timesteps=20).eval()
+    g = torch.Generator().manual_seed(99)
+    clean = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    noisy = (clean + torch.randn(2, 3, 64, 64, generator=g) * (25 / 127.5)).clamp(-1, 1)
+    with torch.no_grad():
+        ref = orc.improved_sampling(dm.state_dict(), noisy, 20)
+    dm = dm.to(DEV)
+    for precision, bound in (("bf16x2", None), ("bf16x3", 1e-4)):
+        dm.precision = precision
+        got = dm.improved_sampling(noisy.to(DEV)).cpu()
+        frac, mx = _check_bar(got, ref, clean, what=f"20-step sampler {precision}")
+        if bound:
+            assert mx <= bound, f"{precision}: max err {mx:.3e}"
+
+
+def test_module_contract(built_lib):
+    net = b2.RDUNet(base_filters=16).to(DEV).eval()
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="divisible by 8"):
+            net(torch.zeros(1, 3, 20, 32, device=DEV))
+        with pytest.raises(RuntimeError, match="channels"):
+            net(torch.zeros(1, 4, 16, 16, device=DEV))
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            net(torch.zeros(1, 3, 16, 16))
+        x = torch.rand(2, 3, 16, 16, device=DEV)
+        y0 = net(x)
+        # load_state_dict must invalidate packed weights
+        sd = {k: v.clone() for k, v in net.state_dict().items()}
+        sd["output_block.conv_2.bias"] += 1.0
+        net.load_state_dict(sd)
+        y1 = net(x)
+        assert float((y1 - y0).abs().min()) > 0.1
+        for k in sd:
+            if k.endswith("conv_2.weight") and k.startswith("output_block"):
+                sd[k] = sd[k] * 0
+        net.load_state_dict(sd)
+        y2 = net(x)
+        # zero output conv -> out = prelu(bias) + x
+        b = sd["output_block.conv_2.bias"].to(DEV)
+        a = sd["output_block.actv_2.weight"].to(DEV)
+        expect = torch.where(b > 0, b, a * b).view(1, 3, 1, 1) + x
+        assert float((y2 - expect).abs().max()) < 1e-6
+    with pytest.raises(RuntimeError, match="inference-only"):
+        net.train()(torch.rand(1, 3, 16, 16, device=DEV))
+
+
+def test_linearity_of_sampler_step_and_idempotent_shapes(built_lib):
+    """Size-independent property at BASELINE size: zero networks make the sampler an exact identity chain."""
+    dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=16), timesteps=20).to(DEV).eval()
+    with torch.no_grad():
+        for p in dm.parameters():
+            p.zero_()
+    y = torch.rand(16, 3, 256, 256, device=DEV) * 2 - 1
+    out = dm.improved_sampling(y)
+    # U(x,t) = 0 + x  =>  x_{t-1} = x - ((1-a_t) x + a_t y) + ((1-a_p) x + a_p y); with x_T = y every step returns y
+    # up to fp32 rounding of the reference's operation order — which the oracle reproduces exactly.
+    x = y.cpu()
+    for t in range(20, 0, -1):
+        x = orc.sampler_step(x, x, x, y.cpu(), t, 20)
+    assert torch.equal(out.cpu(), x)

@@ -1,0 +1,129 @@
+// conv_in.cu — InputBlock.conv_1 + actv_1 (UNet/RDUNet_model.py:71-81) fused with the module-boundary
+// ingest: reads the caller's fp32 NCHW image (and, for RDUNet_T, the broadcast timestep plane that the
+// reference concatenates at diffusion_denoising/Unet/Unet_model.py:135-136), writes NHWC 16-bit planes.
+// K = 27 or 36 is far too small for the tensor pipe and the layer is bandwidth-bound (AI ~ 26 FLOP/B),
+// so this runs on CUDA cores in fp32.
+#include "common.cuh"
+
+namespace b200dn {
+
+namespace {
+
+constexpr int PX = 32;  // pixels along W per block
+
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int Bx, const float* __restrict__ t,
+                                                      int64_t t_sb, int64_t t_sh, int64_t t_sw, int H, int W, int cout,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      const float* __restrict__ slope, int prec,
+                                                      uint16_t* __restrict__ out0, uint16_t* __restrict__ out1,
+                                                      int out_ctot) {
+  extern __shared__ float w_s[];  // [CIN*9][cout]
+  constexpr int K = CIN * 9;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthr = blockDim.x * blockDim.y;
+  for (int i = tid; i < K * cout; i += nthr) {
+    const int o = i / K, k = i - o * K;  // w is [o][ci][ky][kx] = [o][k]
+    w_s[k * cout + o] = w[i];
+  }
+  __syncthreads();
+
+  const int b = blockIdx.z;
+  const int y = blockIdx.y;
+  const int xx = blockIdx.x * PX + threadIdx.x;
+  if (xx >= W) return;
+  const int64_t hw = static_cast<int64_t>(H) * W;
+  const float* xb = x + static_cast<int64_t>(b % Bx) * 3 * hw;
+
+  float v[K];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xc = xx + kx - 1;
+      const bool in = (yy >= 0) && (yy < H) && (xc >= 0) && (xc < W);
+      const int64_t sp = static_cast<int64_t>(yy) * W + xc;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) v[ci * 9 + ky * 3 + kx] = in ? __ldg(xb + ci * hw + sp) : 0.f;
+      if (CIN == 4) v[27 + ky * 3 + kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
+    }
+  }
+
+  const int64_t pix = (static_cast<int64_t>(b) * H + y) * W + xx;
+  const bool is_bf16 = prec != B200DN_PREC_FP16;
+  for (int g = threadIdx.y; g * 8 < cout; g += blockDim.y) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8 + 4);
+      acc[0] = fmaf(v[k], w0.x, acc[0]);
+      acc[1] = fmaf(v[k], w0.y, acc[1]);
+      acc[2] = fmaf(v[k], w0.z, acc[2]);
+      acc[3] = fmaf(v[k], w0.w, acc[3]);
+      acc[4] = fmaf(v[k], w1.x, acc[4]);
+      acc[5] = fmaf(v[k], w1.y, acc[5]);
+      acc[6] = fmaf(v[k], w1.z, acc[6]);
+      acc[7] = fmaf(v[k], w1.w, acc[7]);
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = acc[2 * j] + __ldg(bias + g * 8 + 2 * j);
+      float c = acc[2 * j + 1] + __ldg(bias + g * 8 + 2 * j + 1);
+      a = a > 0.f ? a : a * __ldg(slope + g * 8 + 2 * j);
+      c = c > 0.f ? c : c * __ldg(slope + g * 8 + 2 * j + 1);
+      if (is_bf16) {
+        hi[j] = pack_bf16x2(a, c);
+        lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), c - bf16_hi(hi[j]));
+      } else {
+        hi[j] = pack_f16x2(a, c);
+        lo[j] = 0;
+      }
+    }
+    *reinterpret_cast<uint4*>(out0 + pix * out_ctot + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (out1 != nullptr) *reinterpret_cast<uint4*>(out1 + pix * out_ctot + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+}  // namespace
+}  // namespace b200dn
+
+extern "C" int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_sb, int64_t t_sh, int64_t t_sw, int B,
+                              int H, int W, int cout, const float* w, const float* bias, const float* slope, int prec,
+                              void* out0, void* out1, int out_ctot, void* stream) {
+  using namespace b200dn;
+  B200DN_CHECK_ARG(x && w && bias && slope && out0, "conv_in: null pointer");
+  B200DN_CHECK_ARG(B > 0 && Bx > 0 && H > 0 && W > 0, "conv_in: non-positive dims");
+  B200DN_CHECK_ARG(cout > 0 && cout % 8 == 0, "conv_in: cout %d must be a multiple of 8", cout);
+  B200DN_CHECK_ARG(out_ctot % 8 == 0 && out_ctot >= cout, "conv_in: out_ctot %d invalid", out_ctot);
+  B200DN_CHECK_ARG(prec >= 0 && prec <= 3, "conv_in: bad prec %d", prec);
+  const bool two = (prec == B200DN_PREC_BF16X2 || prec == B200DN_PREC_BF16X3);
+  B200DN_CHECK_ARG(!two || out1, "conv_in: prec %d needs the lo output plane", prec);
+  B200DN_CHECK_ARG(B <= 65535 && H <= 65535, "conv_in: B/H exceed the grid limit");
+  if (int rc = require_sm100()) return rc;
+  const int cin = t ? 4 : 3;
+  const size_t smem = static_cast<size_t>(cin) * 9 * cout * sizeof(float);
+  B200DN_CHECK_ARG(smem <= 160 * 1024, "conv_in: cout %d too large", cout);
+  int ny = cout / 8;
+  if (ny > 8) ny = 8;
+  dim3 block(PX, ny), grid(cdiv(W, PX), H, B);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint16_t* o0 = static_cast<uint16_t*>(out0);
+  uint16_t* o1 = two ? static_cast<uint16_t*>(out1) : nullptr;
+  if (cin == 4) {
+    if (smem > 48 * 1024)
+      B200DN_CUDA(cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_in_kernel<4><<<grid, block, smem, s>>>(x, Bx, t, t_sb, t_sh, t_sw, H, W, cout, w, bias, slope, prec, o0, o1,
+                                                out_ctot);
+  } else {
+    if (smem > 48 * 1024)
+      B200DN_CUDA(cudaFuncSetAttribute(conv_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_in_kernel<3><<<grid, block, smem, s>>>(x, Bx, nullptr, 0, 0, 0, H, W, cout, w, bias, slope, prec, o0, o1,
+                                                out_ctot);
+  }
+  B200DN_CUDA(cudaGetLastError());
+  return 0;
+}

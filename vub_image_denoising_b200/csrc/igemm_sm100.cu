@@ -1,0 +1,563 @@
+// igemm_sm100.cu — the tcgen05/TMEM implicit-GEMM convolution of the RDUNet hot path.
+//
+// One persistent, warp-specialised kernel covers every GEMM-shaped layer of the network
+// (reference: UNet/RDUNet_model.py:49-115, diffusion_denoising/Unet/Unet_model.py:23-89):
+//
+//   CONV3X3  D[pix, co] = sum_{tap,ci} X[pix + (dy,dx), ci] * W[tap][co][ci]       (zero pad 1)
+//   DOWN2X2  D[opix, co] = sum_{ky,kx,ci} X[2*opix + (ky,kx), ci] * W[tap][co][ci]
+//   UP2X2    D[pix, (ky,kx,co)] = sum_ci X[pix, ci] * Wt[ky*2+kx][co][ci]  -> scattered to (2y+ky, 2x+kx)
+//
+// Layout: activations NHWC 16-bit (bf16 or fp16), one or two planes (hi, lo); a layer reads the channel
+// prefix [0,cin) of its input buffer and writes the channel slice [coff, coff+cout) of its output buffer,
+// so the dense-block concatenations of the reference never materialise.
+//
+// Pipeline per CTA (256 threads, 1 CTA/SM, grid = #SMs, static round-robin tile schedule):
+//   warp 0 / lane 0 : TMA producer.  Per K step (pair, tap, 64-channel block) one haloed A box
+//                     [8 x 16 pixels x 64 ch] (OOB zero fill == conv padding) and one W box [N x 64] land
+//                     in a 128B-swizzled smem ring stage and complete on its mbarrier.
+//   warp 1 / lane 0 : MMA issuer.  tcgen05.mma.cta_group::1.kind::f16, M=128, N=block_n, K=16, fp32
+//                     accumulator in TMEM (2 accumulator stages so the epilogue overlaps the next tile).
+//   warp 2          : TMEM allocator.
+//   warps 4..7      : epilogue.  tcgen05.ld -> +bias -> PReLU -> (+residual) -> 16-bit planes into the
+//                     NHWC channel slice, or fp32 NCHW (+fp32 NCHW residual) for the output block.
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace b200dn {
+
+namespace {
+
+constexpr int TILE_W = 16;
+constexpr int TILE_H = 8;
+constexpr int BLOCK_M = TILE_W * TILE_H;  // 128 = UMMA M
+constexpr int BLOCK_K = 64;               // 64 x 16-bit = one 128-byte swizzle row
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int RING_BYTES = 192 * 1024;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_N = 256;
+constexpr int MISC_BYTES = 256 + 4 * MAX_N * 4 * 1;  // barriers + tmem ptr, then bias/slope [2][256] each
+constexpr int SMEM_BYTES = 1024 + RING_BYTES + 256 + 2 * 2 * MAX_N * 4;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+
+struct __align__(64) KParams {
+  CUtensorMap tmA0, tmA1, tmW;
+  int mode, taps;
+  int B, H, W;  // GEMM-M domain (pixels the accumulator rows enumerate)
+  int cin, n_cblk, last_k16;
+  int cout, block_n;
+  int n_tiles_per_group, n_groups, num_n_tiles;
+  int tiles_x, tiles_y, num_m_tiles, num_tiles;
+  int n_pairs, pair_a[3], pair_w[3];
+  int wgroups;
+  int fmt;  // 1 bf16, 0 fp16
+  int num_stages, stage_bytes, tmem_cols;
+  const float* bias;
+  const float* slope;
+  int out_kind;
+  void* out0;
+  void* out1;
+  int out_ctot, out_coff;
+  const void* res0;
+  const void* res1;
+  int res_ctot;
+  float* out_nchw;
+  const float* res_nchw;
+  int res_bmod;
+};
+
+struct TileCoord {
+  int b, y0, x0, grp, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
+  TileCoord t;
+  const int m_tile = tile / p.num_n_tiles;
+  const int nt = tile - m_tile * p.num_n_tiles;
+  t.grp = nt / p.n_tiles_per_group;
+  t.n0 = (nt - t.grp * p.n_tiles_per_group) * p.block_n;
+  const int per_img = p.tiles_x * p.tiles_y;
+  t.b = m_tile / per_img;
+  const int r = m_tile - t.b * per_img;
+  const int ty = r / p.tiles_x;
+  t.y0 = ty * TILE_H;
+  t.x0 = (r - ty * p.tiles_x) * TILE_W;
+  return t;
+}
+
+template <bool kBf16>
+__device__ __forceinline__ float cvt_lo(uint32_t v) {
+  return kBf16 ? bf16_lo(v) : f16_lo(v);
+}
+template <bool kBf16>
+__device__ __forceinline__ float cvt_hi(uint32_t v) {
+  return kBf16 ? bf16_hi(v) : f16_hi(v);
+}
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  return kBf16 ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+}
+template <bool kBf16>
+__device__ __forceinline__ float round16(float a) {
+  return kBf16 ? __bfloat162float(__float2bfloat16_rn(a)) : __half2float(__float2half_rn(a));
+}
+
+// 16 accumulator columns of one pixel -> 16 channels of the NHWC slice.
+template <bool kBf16>
+__device__ __forceinline__ void epilogue_nhwc16(const KParams& p, float (&v)[16], int64_t out_pix, int64_t res_pix,
+                                                int ch0, bool valid) {
+  if (!valid || ch0 >= p.cout) return;
+  const bool half1 = (ch0 + 8) < p.cout;  // second 8-channel group inside cout
+  if (p.res0 != nullptr) {
+    const uint4* r0 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res0) + res_pix * p.res_ctot + ch0);
+    uint4 q[2];
+    q[0] = __ldg(r0);
+    q[1] = half1 ? __ldg(r0 + 1) : make_uint4(0, 0, 0, 0);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[2 * j] += cvt_lo<kBf16>(w[j]);
+      v[2 * j + 1] += cvt_hi<kBf16>(w[j]);
+    }
+    if (p.res1 != nullptr) {
+      const uint4* r1 =
+          reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res1) + res_pix * p.res_ctot + ch0);
+      q[0] = __ldg(r1);
+      q[1] = half1 ? __ldg(r1 + 1) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[2 * j] += cvt_lo<kBf16>(w[j]);
+        v[2 * j + 1] += cvt_hi<kBf16>(w[j]);
+      }
+    }
+  }
+  uint32_t hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hi[j] = pack2<kBf16>(v[2 * j], v[2 * j + 1]);
+  uint4* o0 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out0) + out_pix * p.out_ctot + p.out_coff + ch0);
+  o0[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (half1) o0[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  if (p.out1 != nullptr) {
+    uint32_t lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = v[2 * j] - cvt_lo<kBf16>(hi[j]);
+      const float b = v[2 * j + 1] - cvt_hi<kBf16>(hi[j]);
+      lo[j] = pack2<kBf16>(a, b);
+    }
+    uint4* o1 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out1) + out_pix * p.out_ctot + p.out_coff + ch0);
+    o1[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (half1) o1[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
+  const uint32_t bars = smem_base + RING_BYTES;
+  // barrier map: full[8] @0, empty[8] @64, tmem_full[2] @128, tmem_empty[2] @144, tmem ptr @160
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + RING_BYTES + 160);
+  float* epi_bias = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256);  // [2][MAX_N]
+  float* epi_slope = epi_bias + 2 * MAX_N;                                  // [2][MAX_N]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmW);
+    if (p.n_pairs > 1) tma_prefetch_desc(&p.tmA1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(bars + s * 8, 1);
+      mbar_init(bars + 64 + s * 8, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bars + 128 + a * 8, 1);
+      mbar_init(bars + 144 + a * 8, EPI_THREADS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_s), static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int k_iters = p.n_pairs * p.taps * p.n_cblk;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================================================== TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(A_BYTES + p.block_n * 128);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int pair = 0; pair < p.n_pairs; ++pair) {
+          const CUtensorMap* tmA = p.pair_a[pair] ? &p.tmA1 : &p.tmA0;
+          const int wbase = p.pair_w[pair] * p.wgroups;
+          for (int tap = 0; tap < p.taps; ++tap) {
+            for (int cb = 0; cb < p.n_cblk; ++cb) {
+              mbar_wait(bars + 64 + stage * 8, phase ^ 1u);
+              const uint32_t full = bars + stage * 8;
+              const uint32_t a_dst = smem_base + stage * p.stage_bytes;
+              mbar_arrive_expect_tx(full, tx_bytes);
+              if (p.mode == B200DN_MODE_CONV3X3) {
+                const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                tma_load_4d(a_dst, tmA, full, cb * BLOCK_K, t.x0 + dx, t.y0 + dy, t.b);
+              } else if (p.mode == B200DN_MODE_DOWN2X2) {
+                tma_load_5d(a_dst, tmA, full, cb * BLOCK_K, tap & 1, t.x0, tap >> 1, t.y0);
+              } else {
+                tma_load_4d(a_dst, tmA, full, cb * BLOCK_K, t.x0, t.y0, t.b);
+              }
+              const int wslice = wbase + (p.mode == B200DN_MODE_UP2X2 ? t.grp : tap);
+              tma_load_3d(a_dst + A_BYTES, &p.tmW, full, cb * BLOCK_K, t.n0, wslice);
+              if (++stage == p.num_stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================================================== MMA issuer
+      const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.fmt), static_cast<uint32_t>(p.block_n));
+      int stage = 0;
+      uint32_t phase = 0;
+      int local_tile = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local_tile) {
+        const int acc = local_tile & 1;
+        const uint32_t acc_phase = (local_tile >> 1) & 1;
+        mbar_wait(bars + 144 + acc * 8, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.block_n);
+        uint32_t accumulate = 0;
+        int cb = 0;
+        for (int kit = 0; kit < k_iters; ++kit) {
+          const int nk16 = (cb == p.n_cblk - 1) ? p.last_k16 : (BLOCK_K / 16);
+          mbar_wait(bars + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * p.stage_bytes;
+          const uint64_t adesc = make_sw128_desc(a_addr, 1024);
+          const uint64_t bdesc = make_sw128_desc(a_addr + A_BYTES, 1024);
+          for (int k = 0; k < nk16; ++k) {
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+            accumulate = 1;
+          }
+          umma_commit(bars + 64 + stage * 8);  // frees the smem stage once these MMAs retire
+          if (++stage == p.num_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          if (++cb == p.n_cblk) cb = 0;
+        }
+        umma_commit(bars + 128 + acc * 8);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================================= epilogue
+    const int we = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = we * 32 + lane;
+    const int th = row / TILE_W, tw = row - th * TILE_W;
+    const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);
+    const bool is_bf16 = p.fmt != 0;
+    int local_tile = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local_tile) {
+      const TileCoord t = decode_tile(p, tile);
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = (local_tile >> 1) & 1;
+      float* bs = epi_bias + acc * MAX_N;
+      float* ss = epi_slope + acc * MAX_N;
+      for (int i = et; i < p.block_n; i += EPI_THREADS) {
+        const int c = t.n0 + i;
+        bs[i] = (c < p.cout) ? __ldg(p.bias + c) : 0.f;
+        ss[i] = (p.slope != nullptr && c < p.cout) ? __ldg(p.slope + c) : 1.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+
+      mbar_wait(bars + 128 + acc * 8, acc_phase);
+      tc_fence_after();
+
+      const int y = t.y0 + th, x = t.x0 + tw;
+      const bool valid = (y < p.H) && (x < p.W);
+      int64_t out_pix, res_pix;
+      res_pix = (static_cast<int64_t>(t.b) * p.H + y) * p.W + x;
+      if (p.mode == B200DN_MODE_UP2X2) {
+        const int ky = t.grp >> 1, kx = t.grp & 1;
+        out_pix = (static_cast<int64_t>(t.b) * (2 * p.H) + (2 * y + ky)) * (2 * p.W) + (2 * x + kx);
+      } else {
+        out_pix = res_pix;
+      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>(acc * p.block_n);
+
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (c0 + 16 >= p.block_n) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(bars + 144 + acc * 8);
+        }
+        float v[16];
+        const float4* b4 = reinterpret_cast<const float4*>(bs + c0);
+        const float4* s4 = reinterpret_cast<const float4*>(ss + c0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 bb = b4[q];
+          const float4 sl = s4[q];
+          float a;
+          a = __uint_as_float(r[4 * q + 0]) + bb.x;
+          v[4 * q + 0] = a > 0.f ? a : a * sl.x;
+          a = __uint_as_float(r[4 * q + 1]) + bb.y;
+          v[4 * q + 1] = a > 0.f ? a : a * sl.y;
+          a = __uint_as_float(r[4 * q + 2]) + bb.z;
+          v[4 * q + 2] = a > 0.f ? a : a * sl.z;
+          a = __uint_as_float(r[4 * q + 3]) + bb.w;
+          v[4 * q + 3] = a > 0.f ? a : a * sl.w;
+        }
+        if (p.out_kind == B200DN_OUT_NHWC16) {
+          if (is_bf16)
+            epilogue_nhwc16<true>(p, v, out_pix, res_pix, t.n0 + c0, valid);
+          else
+            epilogue_nhwc16<false>(p, v, out_pix, res_pix, t.n0 + c0, valid);
+        } else if (valid) {
+          // fp32 NCHW output block: prelu(conv) + inputs   (UNet/RDUNet_model.py:186)
+          const int64_t hw = static_cast<int64_t>(p.H) * p.W;
+          const int64_t sp = static_cast<int64_t>(y) * p.W + x;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = t.n0 + c0 + j;
+            if (c < p.cout) {
+              float o = v[j];
+              if (p.res_nchw != nullptr)
+                o += __ldg(p.res_nchw + (static_cast<int64_t>(t.b % p.res_bmod) * p.cout + c) * hw + sp);
+              p.out_nchw[(static_cast<int64_t>(t.b) * p.cout + c) * hw + sp] = o;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+std::once_flag g_encode_once;
+
+int get_encoder() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  });
+  if (!g_encode) {
+    set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return B200DN_E_CUDA;
+  }
+  return 0;
+}
+
+int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
+           const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(tm, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (rank %d dims %llu %llu %llu %llu %llu)", what,
+              static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              (unsigned long long)(rank > 4 ? dims[4] : 0));
+    return B200DN_E_CUDA;
+  }
+  return 0;
+}
+
+std::once_flag g_attr_once;
+cudaError_t g_attr_err = cudaSuccess;
+
+}  // namespace
+
+int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
+  B200DN_CHECK_ARG(a.mode >= 0 && a.mode <= 3, "igemm: bad mode %d", a.mode);
+  B200DN_CHECK_ARG(a.prec >= 0 && a.prec <= 3, "igemm: bad prec %d", a.prec);
+  B200DN_CHECK_ARG(a.B > 0 && a.H > 0 && a.W > 0 && a.cin > 0 && a.cout > 0, "igemm: non-positive dims");
+  B200DN_CHECK_ARG(a.in[0] && a.wpacked && a.bias, "igemm: null input/weight/bias pointer");
+  B200DN_CHECK_ARG(a.in_ctot % 8 == 0 && a.in_ctot >= a.cin, "igemm: in_ctot %d must be a multiple of 8 and >= cin %d",
+                   a.in_ctot, a.cin);
+  const bool two_a = (a.prec == B200DN_PREC_BF16X2 || a.prec == B200DN_PREC_BF16X3);
+  const bool two_w = (a.prec == B200DN_PREC_BF16X3);
+  B200DN_CHECK_ARG(!two_a || a.in[1], "igemm: prec %d needs the lo activation plane in[1]", a.prec);
+  if (a.mode == B200DN_MODE_DOWN2X2)
+    B200DN_CHECK_ARG(a.H % 2 == 0 && a.W % 2 == 0, "igemm: DOWN2X2 needs even H, W (got %d x %d)", a.H, a.W);
+  if (int rc = require_sm100()) return rc;
+  if (int rc = get_encoder()) return rc;
+
+  KParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = a.mode;
+  p.taps = a.mode == B200DN_MODE_CONV3X3 ? 9 : a.mode == B200DN_MODE_DOWN2X2 ? 4 : 1;
+  p.wgroups = a.mode == B200DN_MODE_CONV3X3 ? 9 : a.mode == B200DN_MODE_CONV1X1 ? 1 : 4;
+  p.n_groups = a.mode == B200DN_MODE_UP2X2 ? 4 : 1;
+  if (a.mode == B200DN_MODE_DOWN2X2) {
+    p.B = 1;
+    p.H = a.B * (a.H / 2);
+    p.W = a.W / 2;
+  } else {
+    p.B = a.B;
+    p.H = a.H;
+    p.W = a.W;
+  }
+  p.cin = a.cin;
+  p.n_cblk = cdiv(a.cin, BLOCK_K);
+  p.last_k16 = cdiv(a.cin - (p.n_cblk - 1) * BLOCK_K, 16);
+  p.cout = a.cout;
+  const int cin_pad = round_up(a.cin, BLOCK_K);
+  const int cout_pad = round_up(a.cout, 16);
+  int block_n = a.block_n;
+  if (block_n == 0) {
+    const int nt = cdiv(cout_pad, MAX_N);
+    block_n = round_up(cdiv(cout_pad, nt), 16);
+  }
+  B200DN_CHECK_ARG(block_n % 16 == 0 && block_n >= 16 && block_n <= MAX_N, "igemm: block_n %d invalid", block_n);
+  p.block_n = block_n;
+  p.n_tiles_per_group = cdiv(cout_pad, block_n);
+  p.num_n_tiles = p.n_tiles_per_group * p.n_groups;
+  p.tiles_x = cdiv(p.W, TILE_W);
+  p.tiles_y = cdiv(p.H, TILE_H);
+  p.num_m_tiles = p.B * p.tiles_x * p.tiles_y;
+  p.num_tiles = p.num_m_tiles * p.num_n_tiles;
+  p.fmt = (a.prec == B200DN_PREC_FP16) ? 0 : 1;
+  switch (a.prec) {
+    case B200DN_PREC_BF16X2:
+      p.n_pairs = 2;
+      p.pair_w[0] = 0, p.pair_a[0] = 1;  // small term first
+      p.pair_w[1] = 0, p.pair_a[1] = 0;
+      break;
+    case B200DN_PREC_BF16X3:
+      p.n_pairs = 3;
+      p.pair_w[0] = 1, p.pair_a[0] = 0;
+      p.pair_w[1] = 0, p.pair_a[1] = 1;
+      p.pair_w[2] = 0, p.pair_a[2] = 0;
+      break;
+    default:
+      p.n_pairs = 1;
+      p.pair_w[0] = 0, p.pair_a[0] = 0;
+  }
+  p.stage_bytes = A_BYTES + block_n * 128;
+  p.num_stages = RING_BYTES / p.stage_bytes;
+  if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
+  int cols = 32;
+  while (cols < 2 * block_n) cols <<= 1;
+  p.tmem_cols = cols;
+
+  p.bias = a.bias;
+  p.slope = a.slope;
+  p.out_kind = a.out_kind;
+  if (a.out_kind == B200DN_OUT_NHWC16) {
+    B200DN_CHECK_ARG(a.out[0], "igemm: null NHWC output");
+    B200DN_CHECK_ARG(!two_a || a.out[1], "igemm: prec %d needs the lo output plane out[1]", a.prec);
+    B200DN_CHECK_ARG(a.out_ctot % 8 == 0 && a.out_coff % 8 == 0 && a.cout % 8 == 0 &&
+                         a.out_coff + a.cout <= a.out_ctot,
+                     "igemm: NHWC output slice [%d,%d) of %d must be 8-channel aligned", a.out_coff,
+                     a.out_coff + a.cout, a.out_ctot);
+    p.out0 = a.out[0];
+    p.out1 = two_a ? a.out[1] : nullptr;
+    p.out_ctot = a.out_ctot;
+    p.out_coff = a.out_coff;
+    if (a.res[0]) {
+      B200DN_CHECK_ARG(a.mode == B200DN_MODE_CONV3X3 || a.mode == B200DN_MODE_CONV1X1,
+                       "igemm: NHWC residual only with stride-1 modes");
+      B200DN_CHECK_ARG(a.res_ctot % 8 == 0 && a.res_ctot >= a.cout, "igemm: bad res_ctot %d", a.res_ctot);
+      B200DN_CHECK_ARG(!two_a || a.res[1], "igemm: prec %d needs the lo residual plane", a.prec);
+      p.res0 = a.res[0];
+      p.res1 = two_a ? a.res[1] : nullptr;
+      p.res_ctot = a.res_ctot;
+    }
+  } else if (a.out_kind == B200DN_OUT_NCHW32) {
+    B200DN_CHECK_ARG(a.out_nchw, "igemm: null NCHW output");
+    B200DN_CHECK_ARG(a.mode == B200DN_MODE_CONV3X3 || a.mode == B200DN_MODE_CONV1X1,
+                     "igemm: NCHW output only with stride-1 modes");
+    p.out_nchw = a.out_nchw;
+    p.res_nchw = a.res_nchw;
+    p.res_bmod = a.res_bmod > 0 ? a.res_bmod : a.B;
+  } else {
+    B200DN_CHECK_ARG(false, "igemm: bad out_kind %d", a.out_kind);
+  }
+
+  // ---- tensor maps
+  const CUtensorMapDataType dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const uint64_t ct = static_cast<uint64_t>(a.in_ctot);
+  for (int pl = 0; pl < (two_a ? 2 : 1); ++pl) {
+    CUtensorMap* tm = pl ? &p.tmA1 : &p.tmA0;
+    B200DN_CHECK_ARG((reinterpret_cast<uintptr_t>(a.in[pl]) & 15) == 0, "igemm: input plane %d not 16-byte aligned", pl);
+    if (a.mode == B200DN_MODE_DOWN2X2) {
+      // (c, kx, ox, ky, b*Ho+oy): address = ((2*oy'+ky)*W + 2*ox+kx)*ctot + c
+      uint64_t dims[5] = {static_cast<uint64_t>(a.cin), 2, static_cast<uint64_t>(a.W / 2), 2,
+                          static_cast<uint64_t>(a.B) * (a.H / 2)};
+      uint64_t str[4] = {ct * 2, 2 * ct * 2, static_cast<uint64_t>(a.W) * ct * 2, 2 * static_cast<uint64_t>(a.W) * ct * 2};
+      uint32_t box[5] = {BLOCK_K, 1, TILE_W, 1, TILE_H};
+      if (int rc = encode(tm, dt, 5, a.in[pl], dims, str, box, "A/down")) return rc;
+    } else {
+      uint64_t dims[4] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
+                          static_cast<uint64_t>(a.B)};
+      uint64_t str[3] = {ct * 2, static_cast<uint64_t>(a.W) * ct * 2,
+                         static_cast<uint64_t>(a.H) * static_cast<uint64_t>(a.W) * ct * 2};
+      uint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
+      if (int rc = encode(tm, dt, 4, a.in[pl], dims, str, box, "A")) return rc;
+    }
+  }
+  {
+    B200DN_CHECK_ARG((reinterpret_cast<uintptr_t>(a.wpacked) & 15) == 0, "igemm: packed weights not 16-byte aligned");
+    uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(cout_pad),
+                        static_cast<uint64_t>(p.wgroups) * (two_w ? 2 : 1)};
+    uint64_t str[2] = {static_cast<uint64_t>(cin_pad) * 2, static_cast<uint64_t>(cin_pad) * cout_pad * 2};
+    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(block_n), 1};
+    if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
+  }
+
+  std::call_once(g_attr_once, [] {
+    g_attr_err = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(igemm_kernel, smem)");
+
+  int sms = device_sm_count();
+  if (sms <= 0) return B200DN_E_CUDA;
+  int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
+  igemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  B200DN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200dn
+
+extern "C" int b200dn_igemm(const b200dn_igemm_args* args, void* stream) {
+  if (!args) {
+    b200dn::set_error("igemm: null args");
+    return B200DN_E_ARG;
+  }
+  return b200dn::igemm_launch(*args, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,439 @@
+"""Drop-in RDUNet / RDUNet_T modules whose forward runs on the hand-written sm_100a kernels.
+
+Reference interface mirrored here (pierregab/VUB_Image_denoising):
+  * ``RDUNet(channels=3, base_filters=64).forward(inputs)``            UNet/RDUNet_model.py:117-186
+  * ``RDUNet_T(channels=4, base_filters=64).forward(inputs, t)``       diffusion_denoising/Unet/Unet_model.py:92-166
+  * ``init_weights(init_type='xavier')``                               UNet/RDUNet_model.py:30-47
+  * the 207-tensor ``state_dict`` (names, shapes, fp32, registration order) — so reference
+    checkpoints load unchanged and ``torch.manual_seed(s); RDUNet(...)`` draws the same init.
+
+The parameter tree is made of real ``nn.Conv2d`` / ``nn.ConvTranspose2d`` / ``nn.PReLU`` holders whose
+``forward`` is never called.  ``forward`` builds (and caches) a :class:`ForwardPlan`: NHWC 16-bit
+activation buffers laid out so that every ``torch.cat`` of the reference is a channel slice, packed
+tensor-core weights, and the list of C-ABI launches (``b200dn_conv_in`` + 68 ``b200dn_igemm``).
+Inference only; there is no CPU or PyTorch fallback — a CPU tensor raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import IgemmArgs
+
+__all__ = ["RDUNet", "RDUNet_T", "init_weights", "ForwardPlan", "DEFAULT_PREC"]
+
+DEFAULT_PREC = os.environ.get("B200DN_PREC", "bf16")
+
+
+# --------------------------------------------------------------------------- init
+@torch.no_grad()
+def init_weights(init_type: str = "xavier"):
+    """Return an ``nn.Module.apply`` callback (reference: UNet/RDUNet_model.py:30-47).
+
+    Modules whose class name contains ``Conv2d`` get Xavier-normal / Kaiming-normal / orthogonal
+    weights; ``ConvTranspose2d`` does not contain that substring, so — as in the reference —
+    transposed convolutions and all biases keep PyTorch's defaults.
+    """
+    fill = {"xavier": nn.init.xavier_normal_, "he": nn.init.kaiming_normal_}.get(init_type, nn.init.orthogonal_)
+
+    def visit(module: nn.Module) -> None:
+        kind = type(module).__name__
+        if "Conv2d" in kind:
+            fill(module.weight)
+        elif "BatchNorm" in kind:
+            nn.init.normal_(module.weight, 1.0, 0.01)
+            nn.init.zeros_(module.bias)
+
+    return visit
+
+
+# --------------------------------------------------------------------------- parameter tree
+class _Params(nn.Module):
+    """Ordered bag of parameter-holding submodules (never executed)."""
+
+    def __init__(self, members: "OrderedDict[str, nn.Module]"):
+        super().__init__()
+        for name, mod in members.items():
+            self.add_module(name, mod)
+
+    def forward(self, *_a, **_k):  # pragma: no cover - guard
+        raise RuntimeError("parameter holder: the fused B200 forward of the owning network must be used")
+
+
+def _conv3(cin: int, cout: int) -> nn.Conv2d:
+    return nn.Conv2d(cin, cout, 3, padding=1)
+
+
+def _io_block(cin: int, cmid: int, cout: int) -> _Params:
+    # registration order conv_1, conv_2, actv_1, actv_2 (UNet/RDUNet_model.py:71-93)
+    return _Params(OrderedDict(conv_1=_conv3(cin, cmid), conv_2=_conv3(cmid, cout),
+                               actv_1=nn.PReLU(cmid), actv_2=nn.PReLU(cout)))
+
+
+def _dense_block(c: int) -> _Params:
+    # conv_0..3 then actv_0..3 (UNet/RDUNet_model.py:95-105); growth g = c // 2
+    g = c // 2
+    members: "OrderedDict[str, nn.Module]" = OrderedDict()
+    for k in range(3):
+        members[f"conv_{k}"] = _conv3(c + k * g, g)
+    members["conv_3"] = _conv3(c + 3 * g, c)
+    for k in range(3):
+        members[f"actv_{k}"] = nn.PReLU(g)
+    members["actv_3"] = nn.PReLU(c)
+    return _Params(members)
+
+
+def _down_block(c: int) -> _Params:
+    return _Params(OrderedDict(conv=nn.Conv2d(c, 2 * c, kernel_size=2, stride=2), actv=nn.PReLU(2 * c)))
+
+
+def _up_block(c_deep: int, c_skip: int, c_out: int) -> _Params:
+    # conv, conv_t, actv, actv_t (UNet/RDUNet_model.py:58-64)
+    return _Params(OrderedDict(conv=_conv3(c_deep + c_skip, c_out),
+                               conv_t=nn.ConvTranspose2d(c_deep, c_deep, 2, stride=2),
+                               actv=nn.PReLU(c_out), actv_t=nn.PReLU(c_deep)))
+
+
+class _RDUNetBase(nn.Module):
+    """Shared wiring of RDUNet and RDUNet_T (they differ in the input conv's Cin and the t plane)."""
+
+    _in_channels: int   # channels seen by input_block.conv_1
+    _img_channels = 3   # channels of the image tensor handed to forward()
+
+    def _build(self, in_channels: int, out_channels: int, base_filters: int) -> None:
+        f = [base_filters * (1 << l) for l in range(4)]
+        self.base_filters = base_filters
+        self._in_channels = in_channels
+        self._out_channels = out_channels
+        self.input_block = _io_block(in_channels, f[0], f[0])
+        self.block_0_0 = _dense_block(f[0])
+        self.block_0_1 = _dense_block(f[0])
+        self.down_0 = _down_block(f[0])
+        self.block_1_0 = _dense_block(f[1])
+        self.block_1_1 = _dense_block(f[1])
+        self.down_1 = _down_block(f[1])
+        self.block_2_0 = _dense_block(f[2])
+        self.block_2_1 = _dense_block(f[2])
+        self.down_2 = _down_block(f[2])
+        self.block_3_0 = _dense_block(f[3])
+        self.block_3_1 = _dense_block(f[3])
+        self.up_2 = _up_block(f[3], f[2], f[2])
+        self.block_2_2 = _dense_block(f[2])
+        self.block_2_3 = _dense_block(f[2])
+        self.up_1 = _up_block(f[2], f[1], f[1])
+        self.block_1_2 = _dense_block(f[1])
+        self.block_1_3 = _dense_block(f[1])
+        self.up_0 = _up_block(f[1], f[0], f[0])
+        self.block_0_2 = _dense_block(f[0])
+        self.block_0_3 = _dense_block(f[0])
+        self.output_block = _io_block(f[0], f[0], out_channels)
+        self.apply(init_weights())
+        # private caches (not parameters / buffers -> invisible to state_dict)
+        self._plans: dict = {}
+        self._packs: dict = {}
+        self.precision = DEFAULT_PREC
+
+    # ---- nn.Module plumbing that must drop caches
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._plans, self._packs = {}, {}
+        return out
+
+    def __deepcopy__(self, memo):
+        import copy
+        plans, packs = self._plans, self._packs
+        self._plans, self._packs = {}, {}
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            for key, val in self.__dict__.items():
+                new.__dict__[key] = copy.deepcopy(val, memo)
+        finally:
+            self._plans, self._packs = plans, packs
+        return new
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_plans"], state["_packs"] = {}, {}
+        return state
+
+    # ---- helpers
+    def _param_signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def plan(self, batch: int, height: int, width: int, precision: Optional[str] = None) -> "ForwardPlan":
+        prec = precision or self.precision
+        key = (batch, height, width, prec)
+        plan = self._plans.get(key)
+        sig = self._param_signature()
+        if plan is None or plan.signature != sig:
+            # drop stale plans (parameters were moved / reloaded); keep at most a few shapes alive
+            if plan is None and len(self._plans) >= 4:
+                self._plans.pop(next(iter(self._plans)))
+            plan = ForwardPlan(self, batch, height, width, prec)
+            plan.signature = sig
+            self._plans[key] = plan
+        return plan
+
+    def _check_input(self, inputs: torch.Tensor) -> torch.Tensor:
+        if not isinstance(inputs, torch.Tensor) or inputs.dim() != 4:
+            raise RuntimeError("expected a 4-D [B, C, H, W] tensor")
+        if not inputs.is_cuda:
+            raise RuntimeError("vub_image_denoising_b200 runs on CUDA (sm_100) tensors only; there is no CPU fallback")
+        if inputs.size(1) != self._img_channels:
+            raise RuntimeError(f"expected input with {self._img_channels} channels, got {inputs.size(1)}")
+        if inputs.size(2) % 8 or inputs.size(3) % 8:
+            raise RuntimeError(f"spatial size {tuple(inputs.shape[2:])} must be divisible by 8 "
+                               "(three stride-2 levels; the reference fails in torch.cat otherwise)")
+        if torch.is_grad_enabled() and (inputs.requires_grad or self.training):
+            raise RuntimeError("the B200 path is inference-only: use model.eval() and torch.no_grad() "
+                               "(training / autograd through the fused kernels is out of scope)")
+        p0 = next(self.parameters())
+        if p0.device != inputs.device:
+            raise RuntimeError(f"module parameters are on {p0.device}, input is on {inputs.device}")
+        return inputs.detach().to(torch.float32).contiguous()
+
+
+class RDUNet(_RDUNetBase):
+    """Residual-dense U-Net, 3-channel in/out (reference: UNet/RDUNet_model.py:117-186)."""
+
+    def __init__(self, channels: int = 3, base_filters: int = 64):
+        super().__init__()
+        self._img_channels = channels
+        self._build(channels, channels, base_filters)
+
+    def forward(self, inputs: torch.Tensor) -> torch.Tensor:
+        x = self._check_input(inputs)
+        with torch.cuda.device(x.device):
+            plan = self.plan(x.size(0), x.size(2), x.size(3))
+            out = torch.empty_like(x)
+            plan.run(x, out)
+        return out
+
+
+class RDUNet_T(_RDUNetBase):
+    """RDUNet with a broadcast timestep plane as 4th input channel
+    (reference: diffusion_denoising/Unet/Unet_model.py:92-166)."""
+
+    def __init__(self, channels: int = 4, base_filters: int = 64):
+        super().__init__()
+        self._img_channels = channels - 1
+        self._build(channels, 3, base_filters)
+
+    def forward(self, inputs: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        x = self._check_input(inputs)
+        if not isinstance(t, torch.Tensor):
+            t = torch.tensor(float(t), device=x.device)
+        t = t.detach().to(device=x.device, dtype=torch.float32)
+        # same broadcast as `t.expand(B, 1, H, W)` at Unet_model.py:135 (raises on incompatible shapes)
+        t_exp = t.expand(x.size(0), 1, x.size(2), x.size(3))
+        with torch.cuda.device(x.device):
+            plan = self.plan(x.size(0), x.size(2), x.size(3))
+            out = torch.empty_like(x)
+            plan.run(x, out, t=t_exp)
+        return out
+
+
+# --------------------------------------------------------------------------- the launch plan
+class _Act:
+    """An NHWC 16-bit activation buffer: one (hi) or two (hi, lo) planes of [B, H, W, ctot]."""
+
+    __slots__ = ("hi", "lo", "ctot", "H", "W")
+
+    def __init__(self, B, H, W, ctot, two, device):
+        self.hi = torch.empty((B, H, W, ctot), dtype=torch.int16, device=device)
+        self.lo = torch.empty((B, H, W, ctot), dtype=torch.int16, device=device) if two else None
+        self.ctot, self.H, self.W = ctot, H, W
+
+    def ptrs(self):
+        return self.hi.data_ptr(), (self.lo.data_ptr() if self.lo is not None else None)
+
+
+class ForwardPlan:
+    """Buffers + packed weights + the ordered C-ABI launch list of one (B, H, W, precision) forward.
+
+    Buffer plan per level l (C = F*2^l channels, g = C/2): two dense buffers ``Da, Db`` of 2.5*C channels
+    (``[x | o0 | o1 | o2]`` — the reference's three torch.cat per DenoisingBlock, RDUNet_model.py:107-113)
+    that ping-pong between consecutive blocks, and for l < 3 a ``K`` buffer of 3*C channels holding
+    ``[skip | upsampled]`` (the torch.cat of UpsampleBlock.forward, RDUNet_model.py:69): the encoder's last
+    block writes ``K[0:C)``, the transposed conv scatters into ``K[C:3C)``.
+    """
+
+    def __init__(self, net: _RDUNetBase, B: int, H: int, W: int, precision: str):
+        if precision not in _lib.PREC_NAMES:
+            raise RuntimeError(f"unknown precision {precision!r}; choose from {sorted(_lib.PREC_NAMES)}")
+        F = net.base_filters
+        if F % 16:
+            raise RuntimeError(f"base_filters={F}: the B200 kernels need a multiple of 16")
+        self.lib = _lib.lib()
+        self.prec = _lib.PREC_NAMES[precision]
+        self.precision = precision
+        self.B, self.H, self.W, self.F = B, H, W, F
+        self.device = next(net.parameters()).device
+        self.two = self.prec in (_lib.PREC_BF16X2, _lib.PREC_BF16X3)
+        self.with_t = net._in_channels == net._img_channels + 1
+        self.out_channels = net._out_channels
+        self.signature = None
+        self._keep = []          # tensors referenced by raw pointer from the arg blocks
+        self.launches = []       # list[IgemmArgs]
+        self.flops = 0
+        dev = self.device
+        with torch.cuda.device(dev):
+            self._build(net)
+
+    # ---- weights
+    def _pack(self, conv: nn.Module, transposed: bool = False) -> torch.Tensor:
+        w = conv.weight.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+            self._keep.append(w)
+        if transposed:
+            cin, cout, groups = w.shape[0], w.shape[1], 4
+        else:
+            cout, cin, groups = w.shape[0], w.shape[1], w.shape[2] * w.shape[3]
+        nbytes = self.lib.b200dn_packed_weight_bytes(cout, cin, groups, self.prec)
+        packed = torch.empty(nbytes // 2, dtype=torch.int16, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if transposed:
+            rc = self.lib.b200dn_pack_convt_weight(w.data_ptr(), cin, cout, self.prec, packed.data_ptr(), stream)
+        else:
+            rc = self.lib.b200dn_pack_conv_weight(w.data_ptr(), cout, cin, w.shape[2], w.shape[3], self.prec,
+                                                  packed.data_ptr(), stream)
+        _lib.check(rc, "pack weight")
+        self._keep.append(packed)
+        return packed
+
+    @staticmethod
+    def _f32(p: torch.Tensor, keep: list) -> int:
+        t = p.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.float().contiguous()
+        keep.append(t)
+        return t.data_ptr()
+
+    def _igemm(self, mode, conv, actv, src: _Act, cin, dst: Optional[_Act], coff, B, H, W, res: Optional[_Act] = None,
+               transposed=False, nchw=False) -> IgemmArgs:
+        a = IgemmArgs()
+        a.mode, a.prec = mode, self.prec
+        a.B, a.H, a.W = B, H, W
+        cout = conv.weight.shape[1] if transposed else conv.weight.shape[0]
+        a.cin, a.cout = cin, cout
+        hi, lo = src.ptrs()
+        a.in_[0], a.in_[1] = hi, lo
+        a.in_ctot = src.ctot
+        a.wpacked = self._pack(conv, transposed).data_ptr()
+        a.bias = self._f32(conv.bias, self._keep)
+        a.slope = self._f32(actv.weight, self._keep)
+        if nchw:
+            a.out_kind = _lib.OUT_NCHW32
+        else:
+            a.out_kind = _lib.OUT_NHWC16
+            ohi, olo = dst.ptrs()
+            a.out[0], a.out[1] = ohi, olo
+            a.out_ctot, a.out_coff = dst.ctot, coff
+            if res is not None:
+                rhi, rlo = res.ptrs()
+                a.res[0], a.res[1] = rhi, rlo
+                a.res_ctot = res.ctot
+        taps = {_lib.MODE_CONV3X3: 9, _lib.MODE_DOWN2X2: 4, _lib.MODE_UP2X2: 4}[mode]
+        pix = B * H * W if mode != _lib.MODE_DOWN2X2 else B * (H // 2) * (W // 2)
+        self.flops += 2 * pix * taps * cin * cout
+        self.launches.append(a)
+        return a
+
+    def _dense(self, blk: _Params, src: _Act, dst: _Act, dst_coff: int, B, H, W, C) -> None:
+        g = C // 2
+        for k in range(3):
+            self._igemm(_lib.MODE_CONV3X3, getattr(blk, f"conv_{k}"), getattr(blk, f"actv_{k}"),
+                        src, C + k * g, src, C + k * g, B, H, W)
+        # conv_3 + PReLU, then `+ x` (RDUNet_model.py:114-115): residual = channels [0, C) of the block input
+        self._igemm(_lib.MODE_CONV3X3, blk.conv_3, blk.actv_3, src, C + 3 * g, dst, dst_coff, B, H, W, res=src)
+
+    def _build(self, net: _RDUNetBase) -> None:
+        B, H, W, F, dev, two = self.B, self.H, self.W, self.F, self.device, self.two
+        ch = [F << l for l in range(4)]
+        hs = [H >> l for l in range(4)]
+        ws = [W >> l for l in range(4)]
+        Da = [_Act(B, hs[l], ws[l], ch[l] * 5 // 2, two, dev) for l in range(4)]
+        Db = [_Act(B, hs[l], ws[l], ch[l] * 5 // 2, two, dev) for l in range(4)]
+        K = [_Act(B, hs[l], ws[l], ch[l] * 3, two, dev) for l in range(3)]
+        I0 = _Act(B, H, W, F, two, dev)
+        self.bufs = dict(Da=Da, Db=Db, K=K, I0=I0)
+        self.act_bytes = sum(b.hi.numel() * 2 * (2 if two else 1) for b in (*Da, *Db, *K, I0))
+
+        # input block: conv_1 is the CUDA-core ingest kernel (launched separately in run()); conv_2 on tensor cores
+        ib = net.input_block
+        self.in_w = self._f32(ib.conv_1.weight, self._keep)
+        self.in_b = self._f32(ib.conv_1.bias, self._keep)
+        self.in_s = self._f32(ib.actv_1.weight, self._keep)
+        self.flops += 2 * B * H * W * 9 * net._in_channels * F
+        self._igemm(_lib.MODE_CONV3X3, ib.conv_2, ib.actv_2, I0, F, Da[0], 0, B, H, W)
+
+        # encoder
+        for l in range(4):
+            b0, b1 = getattr(net, f"block_{l}_0"), getattr(net, f"block_{l}_1")
+            self._dense(b0, Da[l], Db[l], 0, B, hs[l], ws[l], ch[l])
+            if l < 3:
+                self._dense(b1, Db[l], K[l], 0, B, hs[l], ws[l], ch[l])
+                dn = getattr(net, f"down_{l}")
+                self._igemm(_lib.MODE_DOWN2X2, dn.conv, dn.actv, K[l], ch[l], Da[l + 1], 0, B, hs[l], ws[l])
+            else:
+                self._dense(b1, Db[l], Da[l], 0, B, hs[l], ws[l], ch[l])
+        # decoder
+        for l in (2, 1, 0):
+            up = getattr(net, f"up_{l}")
+            # conv_t + actv_t scatter into K[l][C : 3C); input = Da[l+1][0 : 2C) at half resolution
+            self._igemm(_lib.MODE_UP2X2, up.conv_t, up.actv_t, Da[l + 1], ch[l + 1], K[l], ch[l],
+                        B, hs[l + 1], ws[l + 1], transposed=True)
+            self._igemm(_lib.MODE_CONV3X3, up.conv, up.actv, K[l], 3 * ch[l], Da[l], 0, B, hs[l], ws[l])
+            b2, b3 = getattr(net, f"block_{l}_2"), getattr(net, f"block_{l}_3")
+            self._dense(b2, Da[l], Db[l], 0, B, hs[l], ws[l], ch[l])
+            self._dense(b3, Db[l], Da[l], 0, B, hs[l], ws[l], ch[l])
+        # output block
+        ob = net.output_block
+        self._igemm(_lib.MODE_CONV3X3, ob.conv_1, ob.actv_1, Da[0], F, I0, 0, B, H, W)
+        self.out_args = self._igemm(_lib.MODE_CONV3X3, ob.conv_2, ob.actv_2, I0, F, None, 0, B, H, W, nchw=True)
+        self._refs = [C.byref(a) for a in self.launches]
+
+    # ---- execution
+    def run(self, x: torch.Tensor, out: torch.Tensor, t: Optional[torch.Tensor] = None,
+            x_batch: Optional[int] = None, t_strides=None, t_ptr: Optional[int] = None) -> None:
+        """Enqueue one forward on the current stream.
+
+        x: fp32 NCHW [Bx, 3, H, W] with Bx = x_batch or B; image b of the network batch reads x[b % Bx]
+        (the sampler evaluates the same x_t at two timesteps as one 2B batch).  out: fp32 [B, 3, H, W].
+        t: expanded [B, 1, H, W] view (strides are honoured), or (t_ptr, t_strides) raw.
+        """
+        lib = self.lib
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        bx = x_batch or self.B
+        if self.with_t:
+            if t is not None:
+                sb, _, sh, sw = t.stride()
+                t_ptr, t_strides = t.data_ptr(), (sb, sh, sw)
+            if t_ptr is None:
+                raise RuntimeError("RDUNet_T forward needs the timestep tensor t")
+        else:
+            t_ptr, t_strides = None, (0, 0, 0)
+        I0 = self.bufs["I0"]
+        hi, lo = I0.ptrs()
+        rc = lib.b200dn_conv_in(x.data_ptr(), bx, t_ptr, t_strides[0], t_strides[1], t_strides[2],
+                                self.B, self.H, self.W, self.F, self.in_w, self.in_b, self.in_s, self.prec,
+                                hi, lo, I0.ctot, stream)
+        _lib.check(rc, "conv_in")
+        oa = self.out_args
+        oa.out_nchw = out.data_ptr()
+        oa.res_nchw = x.data_ptr()
+        oa.res_bmod = bx
+        igemm = lib.b200dn_igemm
+        for ref in self._refs:
+            rc = igemm(ref, stream)
+            if rc:
+                _lib.check(rc, "igemm")
