@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of the B200-native RDUNet denoising hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    (the reference's CPU path = the oracle port)
+
+Metric (BASELINE.json): denoised MPix/s, RDUNet(base_filters=128) bf16 inference on batches of 64
+256x256 RGB patches, sigma cycling over {10,20,30,40,50}, PSNR/SSIM evaluated on device.
+One "step" = one batch through the hot path: device noise synthesis from the clean uint8 patches ->
+RDUNet forward (1 CUDA-core ingest conv + 68 tcgen05 implicit-GEMM launches) -> PSNR + SSIM reductions.
+`value` is timed with the clean batch resident in HBM; `e2e` runs the same step from pinned HOST buffers
+with the H2D copy of the patches and the D2H copy of the denoised batch + metrics inside the timed region.
+Each rank processes its own batch (weak scaling, no data-path collective); the metric sums are combined
+by one NCCL all-reduce per step.  A secondary key reports ms per diffusion sample (RDUNet_T(32), T=20).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SIGMAS = (10.0, 20.0, 30.0, 40.0, 50.0)
+PATCH = 256
+MPIX_PER_PATCH = PATCH * PATCH / 1e6
+
+
+def synthetic_clean_u8(batch: int, seed: int = 1234) -> np.ndarray:
+    """Image-like synthetic patches: uniform noise low-passed with a 9x9 box (SURVEY.md §8 d), as uint8 HWC."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(batch, 3, PATCH, PATCH, generator=g)
+    x = torch.nn.functional.pad(x, (4, 4, 4, 4), mode="reflect")
+    x = torch.nn.functional.avg_pool2d(x, 9, stride=1)
+    x = (x - x.amin(dim=(1, 2, 3), keepdim=True)) / (x.amax(dim=(1, 2, 3), keepdim=True) - x.amin(dim=(1, 2, 3), keepdim=True))
+    return (x * 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().numpy()
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm_gbs": d.get("hbm_gbs"),
+                "source": "MEASURED_PEAKS.json (sustained bf16: the kernels are timed inside a long step)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, device: torch.device, period: float = 0.1):
+        super().__init__(daemon=True)
+        self.period = period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(device).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device.index or 0)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def cpu_reference_pass(base_filters: int, batch: int, threads: int, repeats: int, warmup: int, seed: int = 7):
+    """The reference's CPU path for the same step on `batch` patches: numpy/PIL-style noise + RDUNet fp32 forward
+    (oracle port of the reference modules) + host PSNR/SSIM.  Returns (best seconds per step, MPix/s)."""
+    from oracle import metrics_oracle, noise_oracle, rdunet_oracle
+    import vub_image_denoising_b200 as b2
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    sd = b2.RDUNet(base_filters=base_filters).state_dict()       # same seeded random-init weights as the GPU arm
+    clean_u8 = synthetic_clean_u8(batch)
+    sig = np.array([SIGMAS[i % len(SIGMAS)] for i in range(batch)], dtype=np.float32)
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + repeats):
+            t0 = time.perf_counter()
+            _, noisy, clean = noise_oracle.degrade(clean_u8, sig, seed=it)
+            out = rdunet_oracle.rdunet_forward(sd, torch.from_numpy(noisy)).numpy()
+            for i in range(batch):
+                metrics_oracle.calculate_psnr(clean[i], out[i], 1.0)
+                metrics_oracle.structural_similarity(clean[i], out[i], data_range=1.0, channel_axis=0)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    return times, batch * MPIX_PER_PATCH / min(times)
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_batch = 1
+    times, _ = cpu_reference_pass(128, sample_batch, cores, repeats=args.steps, warmup=min(args.warmup, 1))
+    ms = 1e3 * float(np.mean(times))
+    value = sample_batch * MPIX_PER_PATCH / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "denoised_mpix_per_s", "value": value, "unit": "MPix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "RDUNet(base_filters=128) inference, 256x256 RGB patches, sigma in {10..50}, PSNR+SSIM",
+                   "global_batch": sample_batch, "patch": PATCH, "note": "reference CPU path (oracle port of the reference's "
+                   "PyTorch modules + numpy/scipy metrics) on the host cores; each step = 1 patch of the 64-patch batch"},
+        "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_batch} patch per step, mean of {args.steps} steps"},
+        "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ B200 arm
+def run_b200(args) -> None:
+    import torch.distributed as dist
+    import vub_image_denoising_b200 as b2
+    from vub_image_denoising_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 GPU: the product has no CPU path (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, F = args.batch, args.base_filters
+    peaks = load_peaks()
+
+    torch.manual_seed(7)
+    net = b2.RDUNet(base_filters=F).to(dev).eval()
+    net.precision = args.precision
+    clean_host = torch.from_numpy(synthetic_clean_u8(B, seed=1234 + rank)).pin_memory()
+    clean_dev = clean_host.to(dev)
+    sigma = torch.tensor([SIGMAS[i % len(SIGMAS)] for i in range(B)], dtype=torch.float32, device=dev)
+    plan = net.plan(B, PATCH, PATCH)
+    out = torch.empty((B, 3, PATCH, PATCH), dtype=torch.float32, device=dev)
+    out_host = torch.empty((B, 3, PATCH, PATCH), dtype=torch.float32).pin_memory()
+    met_host = torch.empty(3, dtype=torch.float64).pin_memory()
+    acc = sharding.MetricAccumulator(dev)
+    ev_pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+
+    def step(i: int, src_u8: torch.Tensor, events=None):
+        _, noisy, clean = b2.noise.add_gaussian_noise(src_u8, sigma, seed=1000 + i, stream_id=rank, return_u8=False)
+        plan.run(noisy, out, events=events)
+        psnr, ssim = b2.metrics.batch_metrics(clean, out, 1.0)    # evaluate_model.py:50-51 convention
+        acc.update(psnr, ssim)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            step(i, clean_dev)
+        barrier()
+        # ---------------- timed region 1: inputs resident in HBM
+        sampler = ClockSampler(dev)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(i, clean_dev, events=ev_pairs[i])
+        e1.record()
+        barrier()
+        clocks = sampler.finish()
+        ms_total = e0.elapsed_time(e1)
+        # device time of the 68 igemm launches of a step, averaged over the timed steps
+        igemm_last_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs]))
+        red = acc.reduce()                                         # ONE all-reduce of (sum psnr, sum ssim, n)
+        # ---------------- timed region 2: end to end from pinned host buffers
+        for i in range(2):
+            step(i, clean_host.to(dev, non_blocking=True))
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(args.steps):
+            src = clean_host.to(dev, non_blocking=True)            # H2D of this step's patches
+            step(i, src)
+            out_host.copy_(out, non_blocking=True)                 # D2H of the denoised batch
+            met_host.copy_(acc.acc, non_blocking=True)             # D2H of the running metric sums
+        t1.record()
+        barrier()
+        e2e_ms_total = t0.elapsed_time(t1)
+
+    t_ms = torch.tensor([ms_total, e2e_ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total = float(t_ms[0]), float(t_ms[1])
+    ms_step = ms_total / args.steps
+    value = world * B * MPIX_PER_PATCH / (ms_step / 1e3)
+    e2e_value = world * B * MPIX_PER_PATCH / (e2e_ms_total / args.steps / 1e3)
+
+    # roofline of the dominant kernel (igemm_kernel): algorithmic FLOPs of the 68 launches / their device time
+    from oracle import rdunet_oracle
+    flops_img = rdunet_oracle.conv_flops(F)                        # 2*MAC of all 69 convs (SURVEY.md §8 d)
+    flops_in_conv = 2 * 9 * 3 * F * PATCH * PATCH
+    igemm_flops = (flops_img - flops_in_conv) * B
+    achieved = igemm_flops / (igemm_last_ms / 1e3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "igemm_kernel (68 launches per step)", "achieved": achieved,
+                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
+                "traffic": None, "peak_source": peaks["source"],
+                "algorithmic_flops_per_step": igemm_flops, "kernel_ms_per_step": igemm_last_ms,
+                "kernel_share_of_step": igemm_last_ms / ms_step}
+
+    line = {
+        "metric": "denoised_mpix_per_s", "value": value, "unit": "MPix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else args.precision, "data": "synthetic",
+        "config": {"workload": f"RDUNet(base_filters={F}) {args.precision} inference, batch {B} x 256x256 RGB per GPU, "
+                               "sigma cycling {10,20,30,40,50}, noise synthesis + PSNR/SSIM on device",
+                   "global_batch": world * B, "patch": PATCH, "parallelism": f"batch-sharded x{world}, metric all-reduce",
+                   "l2": "working set per step (>= 18 GB of activations) far exceeds the 126 MB L2; no flush needed",
+                   "weights": "random init, torch.manual_seed(7)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "MPix/s", "h2d_bytes_per_step": int(clean_host.numel()),
+                "d2h_bytes_per_step": int(out_host.numel() * 4 + met_host.numel() * 8),
+                "ms_per_step": e2e_ms_total / args.steps},
+        "gpu_launches": args.steps * (1 + 1 + len(plan.launches) + 2),
+        "roofline": roofline,
+        "quality": {"mean_psnr_db": red["psnr"], "mean_ssim": red["ssim"], "images": red["count"]},
+    }
+
+    # ---------------- secondary metric: ms per diffusion sample (RDUNet_T(32), T = 20, batch 16 split over the GPUs)
+    if not args.skip_diffusion:
+        del plan, out, net
+        b2_local = max(1, 16 // world)
+        torch.manual_seed(7)
+        dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=32), timesteps=20).to(dev).eval()
+        _, noisy, _ = b2.noise.add_gaussian_noise(clean_dev[:b2_local].contiguous(), 25.0, seed=5, return_u8=False)
+        for _ in range(2):
+            dm.improved_sampling(noisy)
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        d0.record()
+        for _ in range(reps):
+            dm.improved_sampling(noisy)
+        d1.record()
+        barrier()
+        d_ms = torch.tensor([d0.elapsed_time(d1) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(d_ms, op=dist.ReduceOp.MAX)
+        line["diffusion"] = {"metric": "ms_per_diffusion_sample", "value": float(d_ms[0]) / b2_local, "unit": "ms",
+                             "batch_per_gpu": b2_local, "ms_per_batch": float(d_ms[0]), "timesteps": 20,
+                             "model": "RDUNet_T(base_filters=32)", "precision": dm.precision,
+                             "samples_per_s_all_gpus": world * b2_local / (float(d_ms[0]) / 1e3)}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        cores = os.cpu_count() or 1
+        times, mpix = cpu_reference_pass(F, 1, cores, repeats=2, warmup=1)
+        line["cpu_baseline"] = {"value": mpix, "unit": "MPix/s", "cores": cores, "kind": "port",
+                                "sample": f"1 of the {B} patches per step (RDUNet({F}) fp32 forward + noise + PSNR/SSIM), "
+                                          f"best of 2 after 1 warm-up, {min(times):.2f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--base-filters", type=int, default=128)
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--skip-diffusion", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

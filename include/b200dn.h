@@ -56,6 +56,7 @@ extern "C" {
 #define B200DN_PREC_FP16     1  /* fp16 weights x fp16 activations, 1 MMA          */
 #define B200DN_PREC_BF16X2   2  /* bf16 W x (bf16 hi + bf16 lo) activations, 2 MMA */
 #define B200DN_PREC_BF16X3   3  /* (W hi+lo) x (A hi+lo) minus lo*lo, 3 MMA: fp32 validation build */
+#define B200DN_PREC_FP16X2   4  /* fp16 W x (fp16 hi + fp16 lo) activations, 2 MMA              */
 
 /* implicit-GEMM modes */
 #define B200DN_MODE_CONV3X3  0  /* 3x3, stride 1, zero pad 1 (taps = 9)            */
@@ -93,7 +94,7 @@ typedef struct b200dn_igemm_args {
   int32_t B, H, W;         /* INPUT batch and spatial size (NHWC)                    */
   int32_t cin, cout;       /* logical channels (cout per phase for UP2X2)            */
   /* input activation planes: NHWC, `in_ctot` channels per pixel, the conv reads
-     channels [0, cin).  in[1] is the bf16 "lo" plane (BF16X2/X3), else NULL.        */
+     channels [0, cin).  in[1] is the "lo" plane (BF16X2/X3, FP16X2), else NULL.        */
   const void* in[2];
   int32_t in_ctot;
   const void* wpacked;     /* from b200dn_pack_*                                     */
@@ -113,6 +114,7 @@ typedef struct b200dn_igemm_args {
   int32_t res_bmod;
   int32_t block_n;         /* 0 = auto; else UMMA N (multiple of 16, <= 256)         */
   int32_t max_ctas;        /* 0 = one per SM                                         */
+  int32_t m_tiles;         /* 0 = auto; 1 or 2 A tiles (128 pixels each) per W tile  */
 } b200dn_igemm_args;
 
 int b200dn_igemm(const b200dn_igemm_args* args, void* stream);

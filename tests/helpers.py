@@ -21,11 +21,11 @@ def sd_digest(sd) -> str:
 
 
 def dt16(prec: int):
-    return torch.float16 if prec == _lib.PREC_FP16 else torch.bfloat16
+    return torch.float16 if prec in _lib.FP16_PRECS else torch.bfloat16
 
 
 def two_planes(prec: int) -> bool:
-    return prec in (_lib.PREC_BF16X2, _lib.PREC_BF16X3)
+    return prec in _lib.TWO_PLANE_PRECS
 
 
 def to_planes(x_nchw: torch.Tensor, prec: int, ctot: int | None = None, coff: int = 0):
@@ -74,7 +74,9 @@ def effective_weight(w: torch.Tensor, prec: int) -> torch.Tensor:
 
 def out_tol(ref: torch.Tensor, prec: int) -> torch.Tensor:
     """Per-element tolerance for a 16-bit stored output: 1 ulp of the storage format + fp32 accumulation slack."""
-    if two_planes(prec):
+    if prec == _lib.PREC_FP16X2:
+        rel = 2.0 ** -20
+    elif two_planes(prec):
         rel = 2.0 ** -15
     elif prec == _lib.PREC_FP16:
         rel = 2.0 ** -10

@@ -16,8 +16,8 @@ from vub_image_denoising_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
-PRECS = [_lib.PREC_BF16, _lib.PREC_FP16, _lib.PREC_BF16X2, _lib.PREC_BF16X3]
-PREC_IDS = ["bf16", "fp16", "bf16x2", "bf16x3"]
+PRECS = [_lib.PREC_BF16, _lib.PREC_FP16, _lib.PREC_BF16X2, _lib.PREC_BF16X3, _lib.PREC_FP16X2]
+PREC_IDS = ["bf16", "fp16", "bf16x2", "bf16x3", "fp16x2"]
 
 
 def _rand(*shape, seed, scale=1.0):
@@ -85,8 +85,8 @@ def test_conv3x3_bias_prelu(case, prec, built_lib):
     _check_slice(out_hi, out_lo, prec, coff, cout, ref, "conv3x3")
 
 
-@pytest.mark.parametrize("block_n,max_ctas", [(16, 0), (32, 3), (64, 1), (128, 0)])
-def test_conv3x3_tilings_agree(block_n, max_ctas, built_lib):
+@pytest.mark.parametrize("block_n,max_ctas,m_tiles", [(16, 0, 1), (32, 3, 2), (64, 1, 2), (128, 0, 1), (128, 5, 2), (64, 0, 1)])
+def test_conv3x3_tilings_agree(block_n, max_ctas, m_tiles, built_lib):
     """Different N tilings / CTA counts (multi-tile persistence, TMEM double buffering) give the same bits."""
     prec = _lib.PREC_BF16
     B, H, W, cin, cout = 2, 32, 48, 96, 128
@@ -101,7 +101,7 @@ def test_conv3x3_tilings_agree(block_n, max_ctas, built_lib):
                                 None, None)
     out_hi, _ = _mk_out(B, H, W, cout, prec)
     torch.ops.b200dn.conv_igemm(x_hi, None, wp, bias, slope, _lib.MODE_CONV3X3, prec, cin, cout, out_hi, None, 0,
-                                None, None, block_n, max_ctas)
+                                None, None, block_n, max_ctas, m_tiles)
     torch.cuda.synchronize()
     assert torch.equal(base_hi, out_hi)
 

@@ -74,7 +74,7 @@ def test_rdunet_t_golden(golden, precision, max_abs, built_lib):
 
 
 @pytest.mark.parametrize("use_graph", [True, False])
-@pytest.mark.parametrize("precision,max_abs", [("bf16x2", None), ("bf16x3", 1e-4)])
+@pytest.mark.parametrize("precision,max_abs", [("fp16", None), ("fp16x2", None), ("bf16x2", None), ("bf16x3", 1e-4)])
 def test_sampler_golden(golden, precision, max_abs, use_graph, built_lib):
     torch.manual_seed(13)
     dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=16), timesteps=4)
@@ -123,7 +123,9 @@ def test_eval_width_t32_golden(golden, built_lib):
 
 def test_sampler_full_schedule_vs_oracle(built_lib):
     """Full 20-step schedule, F=32, against the fp32 CPU oracle on a fresh seeded input (64x64 keeps the oracle
-    to a few seconds).  bf16x2 must hold the 99.9%-within-1/255 bar, bf16x3 the 1e-4 bar."""
+    to a few seconds).  The sampler's default 16-bit mode and the fp16 modes must hold the 99.9%-within-1/255
+    bar, bf16x3 the 1e-4 bar.  (bf16 WEIGHT rounding alone breaks the bar on this seed — 99.79% — on the GPU
+    and in a CPU emulation alike, which is why the sampler does not default to a bf16 mode)"""
     torch.manual_seed(3)
     dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=32), timesteps=20).eval()
     g = torch.Generator().manual_seed(99)
@@ -132,7 +134,8 @@ def test_sampler_full_schedule_vs_oracle(built_lib):
     with torch.no_grad():
         ref = orc.improved_sampling(dm.state_dict(), noisy, 20)
     dm = dm.to(DEV)
-    for precision, bound in (("bf16x2", None), ("bf16x3", 1e-4)):
+    assert dm.precision == b2.diffusion.SAMPLER_PREC
+    for precision, bound in ((dm.precision, None), ("fp16", None), ("fp16x2", None), ("bf16x3", 1e-4)):
         dm.precision = precision
         got = dm.improved_sampling(noisy.to(DEV)).cpu()
         frac, mx = _check_bar(got, ref, clean, what=f"20-step sampler {precision}")

@@ -12,9 +12,11 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libb200dn.so"
 
 # enums (mirror include/b200dn.h)
-PREC_BF16, PREC_FP16, PREC_BF16X2, PREC_BF16X3 = 0, 1, 2, 3
+PREC_BF16, PREC_FP16, PREC_BF16X2, PREC_BF16X3, PREC_FP16X2 = 0, 1, 2, 3, 4
 PREC_NAMES = {"bf16": PREC_BF16, "fp16": PREC_FP16, "bf16x2": PREC_BF16X2, "bf16x3": PREC_BF16X3,
-              "fp32": PREC_BF16X3}
+              "fp16x2": PREC_FP16X2, "fp32": PREC_BF16X3}
+TWO_PLANE_PRECS = (PREC_BF16X2, PREC_BF16X3, PREC_FP16X2)
+FP16_PRECS = (PREC_FP16, PREC_FP16X2)
 MODE_CONV3X3, MODE_DOWN2X2, MODE_UP2X2, MODE_CONV1X1 = 0, 1, 2, 3
 OUT_NHWC16, OUT_NCHW32 = 0, 1
 
@@ -41,7 +43,7 @@ class IgemmArgs(C.Structure):
         ("out", C.c_void_p * 2), ("out_ctot", C.c_int32), ("out_coff", C.c_int32),
         ("res", C.c_void_p * 2), ("res_ctot", C.c_int32),
         ("out_nchw", C.c_void_p), ("res_nchw", C.c_void_p), ("res_bmod", C.c_int32),
-        ("block_n", C.c_int32), ("max_ctas", C.c_int32),
+        ("block_n", C.c_int32), ("max_ctas", C.c_int32), ("m_tiles", C.c_int32),
     ]
 
 

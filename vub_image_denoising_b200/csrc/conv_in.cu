@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
 
   const int64_t pix = (static_cast<int64_t>(b) * H + y) * W + xx;
-  const bool is_bf16 = prec != B200DN_PREC_FP16;
+  const bool is_bf16 = (prec != B200DN_PREC_FP16) && (prec != B200DN_PREC_FP16X2);
   for (int g = threadIdx.y; g * 8 < cout; g += blockDim.y) {
     float acc[8];
 #pragma unroll
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
         lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), c - bf16_hi(hi[j]));
       } else {
         hi[j] = pack_f16x2(a, c);
-        lo[j] = 0;
+        lo[j] = pack_f16x2(a - f16_lo(hi[j]), c - f16_hi(hi[j]));
       }
     }
     *reinterpret_cast<uint4*>(out0 + pix * out_ctot + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -99,8 +99,8 @@ extern "C" int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_
   B200DN_CHECK_ARG(B > 0 && Bx > 0 && H > 0 && W > 0, "conv_in: non-positive dims");
   B200DN_CHECK_ARG(cout > 0 && cout % 8 == 0, "conv_in: cout %d must be a multiple of 8", cout);
   B200DN_CHECK_ARG(out_ctot % 8 == 0 && out_ctot >= cout, "conv_in: out_ctot %d invalid", out_ctot);
-  B200DN_CHECK_ARG(prec >= 0 && prec <= 3, "conv_in: bad prec %d", prec);
-  const bool two = (prec == B200DN_PREC_BF16X2 || prec == B200DN_PREC_BF16X3);
+  B200DN_CHECK_ARG(prec >= 0 && prec <= 4, "conv_in: bad prec %d", prec);
+  const bool two = (prec == B200DN_PREC_BF16X2 || prec == B200DN_PREC_BF16X3 || prec == B200DN_PREC_FP16X2);
   B200DN_CHECK_ARG(!two || out1, "conv_in: prec %d needs the lo output plane", prec);
   B200DN_CHECK_ARG(B <= 65535 && H <= 65535, "conv_in: B/H exceed the grid limit");
   if (int rc = require_sm100()) return rc;

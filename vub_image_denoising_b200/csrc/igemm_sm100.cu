@@ -44,12 +44,13 @@ constexpr int EPI_THREADS = 128;
 
 struct __align__(64) KParams {
   CUtensorMap tmA0, tmA1, tmW;
-  int mode, taps;
+  int taps;
   int B, H, W;  // GEMM-M domain (pixels the accumulator rows enumerate)
-  int cin, n_cblk, last_k16;
+  int n_cblk, last_k16;
   int cout, block_n;
-  int n_tiles_per_group, n_groups, num_n_tiles;
-  int tiles_x, tiles_y, num_m_tiles, num_tiles;
+  int mt;       // A tiles (128 pixels each, x-adjacent) sharing one W tile per pipeline stage: 1 or 2
+  int n_tiles_per_group, num_n_tiles;
+  int tiles_x, tiles_y, num_tiles;   // tiles_x counts super tiles (mt * 16 pixels wide)
   int n_pairs, pair_a[3], pair_w[3];
   int wgroups;
   int fmt;  // 1 bf16, 0 fp16
@@ -72,18 +73,19 @@ struct TileCoord {
   int b, y0, x0, grp, n0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const KParams& p, int tile) {
+__device__ __forceinline__ TileCoord decode_tile(int tile, int num_n_tiles, int n_tiles_per_group, int block_n,
+                                                 int tiles_x, int tiles_y, int mt) {
   TileCoord t;
-  const int m_tile = tile / p.num_n_tiles;
-  const int nt = tile - m_tile * p.num_n_tiles;
-  t.grp = nt / p.n_tiles_per_group;
-  t.n0 = (nt - t.grp * p.n_tiles_per_group) * p.block_n;
-  const int per_img = p.tiles_x * p.tiles_y;
+  const int m_tile = tile / num_n_tiles;
+  const int nt = tile - m_tile * num_n_tiles;
+  t.grp = nt / n_tiles_per_group;
+  t.n0 = (nt - t.grp * n_tiles_per_group) * block_n;
+  const int per_img = tiles_x * tiles_y;
   t.b = m_tile / per_img;
   const int r = m_tile - t.b * per_img;
-  const int ty = r / p.tiles_x;
+  const int ty = r / tiles_x;
   t.y0 = ty * TILE_H;
-  t.x0 = (r - ty * p.tiles_x) * TILE_W;
+  t.x0 = (r - ty * tiles_x) * (TILE_W * mt);
   return t;
 }
 
@@ -97,21 +99,29 @@ __device__ __forceinline__ float cvt_hi(uint32_t v) {
 }
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  return kBf16 ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+  if (kBf16) return pack_bf16x2(a, b);
+  // fp16 storage saturates instead of overflowing to inf
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  return pack_f16x2(a, b);
 }
-template <bool kBf16>
-__device__ __forceinline__ float round16(float a) {
-  return kBf16 ? __bfloat162float(__float2bfloat16_rn(a)) : __half2float(__float2half_rn(a));
-}
+
+struct EpiArgs {
+  void* out0;
+  void* out1;
+  const void* res0;
+  const void* res1;
+  int out_ctot, out_coff, res_ctot, cout;
+};
 
 // 16 accumulator columns of one pixel -> 16 channels of the NHWC slice.
 template <bool kBf16>
-__device__ __forceinline__ void epilogue_nhwc16(const KParams& p, float (&v)[16], int64_t out_pix, int64_t res_pix,
-                                                int ch0, bool valid) {
-  if (!valid || ch0 >= p.cout) return;
-  const bool half1 = (ch0 + 8) < p.cout;  // second 8-channel group inside cout
-  if (p.res0 != nullptr) {
-    const uint4* r0 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res0) + res_pix * p.res_ctot + ch0);
+__device__ __forceinline__ void epilogue_nhwc16(const EpiArgs& e, float (&v)[16], int64_t out_pix, int64_t res_pix,
+                                                int ch0) {
+  if (ch0 >= e.cout) return;
+  const bool half1 = (ch0 + 8) < e.cout;  // second 8-channel group inside cout
+  if (e.res0 != nullptr) {
+    const uint4* r0 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(e.res0) + res_pix * e.res_ctot + ch0);
     uint4 q[2];
     q[0] = __ldg(r0);
     q[1] = half1 ? __ldg(r0 + 1) : make_uint4(0, 0, 0, 0);
@@ -121,9 +131,9 @@ __device__ __forceinline__ void epilogue_nhwc16(const KParams& p, float (&v)[16]
       v[2 * j] += cvt_lo<kBf16>(w[j]);
       v[2 * j + 1] += cvt_hi<kBf16>(w[j]);
     }
-    if (p.res1 != nullptr) {
+    if (e.res1 != nullptr) {
       const uint4* r1 =
-          reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.res1) + res_pix * p.res_ctot + ch0);
+          reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(e.res1) + res_pix * e.res_ctot + ch0);
       q[0] = __ldg(r1);
       q[1] = half1 ? __ldg(r1 + 1) : make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -136,10 +146,10 @@ __device__ __forceinline__ void epilogue_nhwc16(const KParams& p, float (&v)[16]
   uint32_t hi[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) hi[j] = pack2<kBf16>(v[2 * j], v[2 * j + 1]);
-  uint4* o0 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out0) + out_pix * p.out_ctot + p.out_coff + ch0);
+  uint4* o0 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(e.out0) + out_pix * e.out_ctot + e.out_coff + ch0);
   o0[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   if (half1) o0[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-  if (p.out1 != nullptr) {
+  if (e.out1 != nullptr) {
     uint32_t lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -147,12 +157,21 @@ __device__ __forceinline__ void epilogue_nhwc16(const KParams& p, float (&v)[16]
       const float b = v[2 * j + 1] - cvt_hi<kBf16>(hi[j]);
       lo[j] = pack2<kBf16>(a, b);
     }
-    uint4* o1 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out1) + out_pix * p.out_ctot + p.out_coff + ch0);
+    uint4* o1 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(e.out1) + out_pix * e.out_ctot + e.out_coff + ch0);
     o1[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     if (half1) o1[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
   }
 }
 
+// MODE: 0 = CONV3X3 (9 taps, shifted 4-D boxes), 1 = DOWN2X2 (4 taps, 5-D map), 2 = UP2X2 / CONV1X1 (one tap)
+// MT:   A tiles (128 pixels each) per W tile and pipeline stage.
+//
+// Warp roles (256 threads): 0 = A-tile TMA producer, 2 = TMEM allocator then W-tile TMA producer,
+// 1 = MMA issuer of sub-tile 0, 3 = MMA issuer of sub-tile 1 (MT == 2), 4..7 = epilogue.
+// ncu showed the single-thread issue loops (uniform-datapath instructions at ~5 cycles each), not the
+// tensor pipe, TMA or L2, bound the first version of this kernel (profiles/r01_igemm_v1_n64.txt); hence
+// two producers, two issuers with independent accumulators, and branch-free inner paths.
+template <int MODE, int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -174,12 +193,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(bars + s * 8, 1);
-      mbar_init(bars + 64 + s * 8, 1);
+      mbar_init(bars + s * 8, 2);        // full: A producer + W producer (each arrive.expect_tx)
+      mbar_init(bars + 64 + s * 8, MT);  // empty: one tcgen05.commit per MMA issuer
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(bars + 128 + a * 8, 1);
-      mbar_init(bars + 144 + a * 8, EPI_THREADS);
+      mbar_init(bars + 128 + a * 8, MT);           // accumulators full: one commit per issuer
+      mbar_init(bars + 144 + a * 8, EPI_THREADS);  // accumulators drained
     }
     mbar_fence_init();
   }
@@ -192,36 +211,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  const int k_iters = p.n_pairs * p.taps * p.n_cblk;
+  // Loop-invariant parameters live in registers: every asm volatile("memory") below would otherwise force the
+  // compiler to re-read them from the constant bank inside the issue loops.
+  const int num_tiles = p.num_tiles, grid = gridDim.x;
+  const int num_n_tiles = p.num_n_tiles, n_tiles_per_group = p.n_tiles_per_group, block_n = p.block_n;
+  const int tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+  const int n_cblk = p.n_cblk, n_pairs = p.n_pairs, num_stages = p.num_stages, stage_bytes = p.stage_bytes;
+  constexpr int KY = MODE == 0 ? 3 : MODE == 1 ? 2 : 1;
+  constexpr int KX = KY;
+  constexpr uint32_t W_OFF = MT * A_BYTES;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================================================== TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(A_BYTES + p.block_n * 128);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        for (int pair = 0; pair < p.n_pairs; ++pair) {
-          const CUtensorMap* tmA = p.pair_a[pair] ? &p.tmA1 : &p.tmA0;
-          const int wbase = p.pair_w[pair] * p.wgroups;
-          for (int tap = 0; tap < p.taps; ++tap) {
-            for (int cb = 0; cb < p.n_cblk; ++cb) {
+    // ===================================================== A-tile TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const int pa0 = p.pair_a[0], pa1 = p.pair_a[1], pa2 = p.pair_a[2];
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
+      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, MT);
+      for (int pair = 0; pair < n_pairs; ++pair) {
+        const int pa = pair == 0 ? pa0 : pair == 1 ? pa1 : pa2;
+        const CUtensorMap* tmA = pa ? &p.tmA1 : &p.tmA0;
+#pragma unroll
+        for (int ky = 0; ky < KY; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < KX; ++kx) {
+            for (int cb = 0; cb < n_cblk; ++cb) {
               mbar_wait(bars + 64 + stage * 8, phase ^ 1u);
-              const uint32_t full = bars + stage * 8;
-              const uint32_t a_dst = smem_base + stage * p.stage_bytes;
-              mbar_arrive_expect_tx(full, tx_bytes);
-              if (p.mode == B200DN_MODE_CONV3X3) {
-                const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-                tma_load_4d(a_dst, tmA, full, cb * BLOCK_K, t.x0 + dx, t.y0 + dy, t.b);
-              } else if (p.mode == B200DN_MODE_DOWN2X2) {
-                tma_load_5d(a_dst, tmA, full, cb * BLOCK_K, tap & 1, t.x0, tap >> 1, t.y0);
-              } else {
-                tma_load_4d(a_dst, tmA, full, cb * BLOCK_K, t.x0, t.y0, t.b);
+              if (elect_one()) {
+                const uint32_t full = bars + stage * 8;
+                const uint32_t a_dst = smem_base + stage * stage_bytes;
+                mbar_arrive_expect_tx(full, MT * A_BYTES);
+#pragma unroll
+                for (int j = 0; j < MT; ++j) {
+                  const int xj = t.x0 + j * TILE_W;
+                  if (MODE == 0)
+                    tma_load_4d(a_dst + j * A_BYTES, tmA, full, cb * BLOCK_K, xj + kx - 1, t.y0 + ky - 1, t.b);
+                  else if (MODE == 1)
+                    tma_load_5d(a_dst + j * A_BYTES, tmA, full, cb * BLOCK_K, kx, xj, ky, t.y0);
+                  else
+                    tma_load_4d(a_dst + j * A_BYTES, tmA, full, cb * BLOCK_K, xj, t.y0, t.b);
+                }
               }
-              const int wslice = wbase + (p.mode == B200DN_MODE_UP2X2 ? t.grp : tap);
-              tma_load_3d(a_dst + A_BYTES, &p.tmW, full, cb * BLOCK_K, t.n0, wslice);
-              if (++stage == p.num_stages) {
+              __syncwarp();
+              if (++stage == num_stages) {
                 stage = 0;
                 phase ^= 1u;
               }
@@ -230,40 +262,83 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================================================== MMA issuer
-      const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.fmt), static_cast<uint32_t>(p.block_n));
-      int stage = 0;
-      uint32_t phase = 0;
-      int local_tile = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local_tile) {
-        const int acc = local_tile & 1;
-        const uint32_t acc_phase = (local_tile >> 1) & 1;
-        mbar_wait(bars + 144 + acc * 8, acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * p.block_n);
-        uint32_t accumulate = 0;
-        int cb = 0;
-        for (int kit = 0; kit < k_iters; ++kit) {
-          const int nk16 = (cb == p.n_cblk - 1) ? p.last_k16 : (BLOCK_K / 16);
-          mbar_wait(bars + stage * 8, phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * p.stage_bytes;
-          const uint64_t adesc = make_sw128_desc(a_addr, 1024);
-          const uint64_t bdesc = make_sw128_desc(a_addr + A_BYTES, 1024);
-          for (int k = 0; k < nk16; ++k) {
-            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-            accumulate = 1;
+  } else if (warp == 2) {
+    // ===================================================== W-tile TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128);
+    const int wg = p.wgroups;
+    const int pw0 = p.pair_w[0] * wg, pw1 = p.pair_w[1] * wg, pw2 = p.pair_w[2] * wg;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
+      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, MT);
+      for (int pair = 0; pair < n_pairs; ++pair) {
+        const int wbase = pair == 0 ? pw0 : pair == 1 ? pw1 : pw2;
+#pragma unroll
+        for (int tap = 0; tap < KY * KX; ++tap) {
+          const int wslice = wbase + (MODE == 2 ? t.grp : tap);
+          for (int cb = 0; cb < n_cblk; ++cb) {
+            mbar_wait(bars + 64 + stage * 8, phase ^ 1u);
+            if (elect_one()) {
+              const uint32_t full = bars + stage * 8;
+              mbar_arrive_expect_tx(full, w_bytes);
+              tma_load_3d(smem_base + stage * stage_bytes + W_OFF, &p.tmW, full, cb * BLOCK_K, t.n0, wslice);
+            }
+            __syncwarp();
+            if (++stage == num_stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
-          umma_commit(bars + 64 + stage * 8);  // frees the smem stage once these MMAs retire
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-          if (++cb == p.n_cblk) cb = 0;
         }
-        umma_commit(bars + 128 + acc * 8);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp == 1 || (warp == 3 && MT == 2)) {
+    // ===================================================== MMA issuer of sub-tile j (independent accumulators)
+    const int j = warp == 1 ? 0 : 1;
+    const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.fmt), static_cast<uint32_t>(block_n));
+    const int k_iters = n_pairs * p.taps * n_cblk;
+    const int last_k16 = p.last_k16;
+    const uint32_t a_off = static_cast<uint32_t>(j * A_BYTES);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local_tile = 0;
+    uint32_t ready = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = (local_tile >> 1) & 1;
+      mbar_wait(bars + 144 + acc * 8, acc_phase ^ 1u);
+      const uint32_t d = tmem_base + static_cast<uint32_t>((acc * MT + j) * block_n);
+      uint32_t accumulate = 0;
+      int cb = 0;
+      for (int kit = 0; kit < k_iters; ++kit) {
+        if (!ready) mbar_wait(bars + stage * 8, phase);
+        tc_fence_after();
+        const uint32_t s_addr = smem_base + stage * stage_bytes;
+        const uint32_t empty_bar = bars + 64 + stage * 8;
+        const bool full_block = (cb != n_cblk - 1) || (last_k16 == BLOCK_K / 16);
+        if (++stage == num_stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        // peek at the next stage's barrier now; its latency hides behind the MMA issue below
+        ready = mbar_test_wait(bars + stage * 8, phase);
+        if (elect_one()) {
+          const uint64_t adesc = make_sw128_desc(s_addr + a_off, 1024);
+          const uint64_t bdesc = make_sw128_desc(s_addr + W_OFF, 1024);
+          if (full_block) {
+            umma_f16(d, adesc, bdesc, idesc, accumulate);
+            umma_f16(d, adesc + 2, bdesc + 2, idesc, 1u);
+            umma_f16(d, adesc + 4, bdesc + 4, idesc, 1u);
+            umma_f16(d, adesc + 6, bdesc + 6, idesc, 1u);
+          } else {
+            for (int k = 0; k < last_k16; ++k) umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? accumulate : 1u);
+          }
+          umma_commit(empty_bar);                                     // frees the smem stage once these MMAs retire
+          if (kit == k_iters - 1) umma_commit(bars + 128 + acc * 8);  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        accumulate = 1;
+        if (++cb == n_cblk) cb = 0;
       }
     }
   } else if (warp >= 4) {
@@ -273,78 +348,90 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     const int th = row / TILE_W, tw = row - th * TILE_W;
     const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);
     const bool is_bf16 = p.fmt != 0;
+    const int H = p.H, W = p.W, cout = p.cout, out_kind = p.out_kind;
+    const float* bias = p.bias;
+    const float* slope = p.slope;
+    EpiArgs ea;
+    ea.out0 = p.out0, ea.out1 = p.out1, ea.res0 = p.res0, ea.res1 = p.res1;
+    ea.out_ctot = p.out_ctot, ea.out_coff = p.out_coff, ea.res_ctot = p.res_ctot, ea.cout = cout;
+    float* out_nchw = p.out_nchw;
+    const float* res_nchw = p.res_nchw;
+    const int res_bmod = p.res_bmod;
+    const bool up = p.wgroups == 4 && MODE == 2;
     int local_tile = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++local_tile) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
+      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, MT);
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (local_tile >> 1) & 1;
       float* bs = epi_bias + acc * MAX_N;
       float* ss = epi_slope + acc * MAX_N;
-      for (int i = et; i < p.block_n; i += EPI_THREADS) {
+      for (int i = et; i < block_n; i += EPI_THREADS) {
         const int c = t.n0 + i;
-        bs[i] = (c < p.cout) ? __ldg(p.bias + c) : 0.f;
-        ss[i] = (p.slope != nullptr && c < p.cout) ? __ldg(p.slope + c) : 1.f;
+        bs[i] = (c < cout) ? __ldg(bias + c) : 0.f;
+        ss[i] = (slope != nullptr && c < cout) ? __ldg(slope + c) : 1.f;
       }
       asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
 
       mbar_wait(bars + 128 + acc * 8, acc_phase);
       tc_fence_after();
 
-      const int y = t.y0 + th, x = t.x0 + tw;
-      const bool valid = (y < p.H) && (x < p.W);
-      int64_t out_pix, res_pix;
-      res_pix = (static_cast<int64_t>(t.b) * p.H + y) * p.W + x;
-      if (p.mode == B200DN_MODE_UP2X2) {
-        const int ky = t.grp >> 1, kx = t.grp & 1;
-        out_pix = (static_cast<int64_t>(t.b) * (2 * p.H) + (2 * y + ky)) * (2 * p.W) + (2 * x + kx);
-      } else {
-        out_pix = res_pix;
-      }
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>(acc * p.block_n);
-
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c0, r);
-        tmem_ld_wait();
-        if (c0 + 16 >= p.block_n) {
-          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(bars + 144 + acc * 8);
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+        const int y = t.y0 + th, x = t.x0 + j * TILE_W + tw;
+        const bool valid = (y < H) && (x < W);
+        const int64_t res_pix = (static_cast<int64_t>(t.b) * H + y) * W + x;
+        int64_t out_pix = res_pix;
+        if (up) {
+          const int ky = t.grp >> 1, kx = t.grp & 1;
+          out_pix = (static_cast<int64_t>(t.b) * (2 * H) + (2 * y + ky)) * (2 * W) + (2 * x + kx);
         }
-        float v[16];
-        const float4* b4 = reinterpret_cast<const float4*>(bs + c0);
-        const float4* s4 = reinterpret_cast<const float4*>(ss + c0);
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n);
+        for (int c0 = 0; c0 < block_n; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          if (j == MT - 1 && c0 + 16 >= block_n) {
+            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warps
+            tc_fence_before();
+            mbar_arrive(bars + 144 + acc * 8);
+          }
+          if (!valid) continue;
+          float v[16];
+          const float4* b4 = reinterpret_cast<const float4*>(bs + c0);
+          const float4* s4 = reinterpret_cast<const float4*>(ss + c0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 bb = b4[q];
-          const float4 sl = s4[q];
-          float a;
-          a = __uint_as_float(r[4 * q + 0]) + bb.x;
-          v[4 * q + 0] = a > 0.f ? a : a * sl.x;
-          a = __uint_as_float(r[4 * q + 1]) + bb.y;
-          v[4 * q + 1] = a > 0.f ? a : a * sl.y;
-          a = __uint_as_float(r[4 * q + 2]) + bb.z;
-          v[4 * q + 2] = a > 0.f ? a : a * sl.z;
-          a = __uint_as_float(r[4 * q + 3]) + bb.w;
-          v[4 * q + 3] = a > 0.f ? a : a * sl.w;
-        }
-        if (p.out_kind == B200DN_OUT_NHWC16) {
-          if (is_bf16)
-            epilogue_nhwc16<true>(p, v, out_pix, res_pix, t.n0 + c0, valid);
-          else
-            epilogue_nhwc16<false>(p, v, out_pix, res_pix, t.n0 + c0, valid);
-        } else if (valid) {
-          // fp32 NCHW output block: prelu(conv) + inputs   (UNet/RDUNet_model.py:186)
-          const int64_t hw = static_cast<int64_t>(p.H) * p.W;
-          const int64_t sp = static_cast<int64_t>(y) * p.W + x;
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = b4[q];
+            const float4 sl = s4[q];
+            float a;
+            a = __uint_as_float(r[4 * q + 0]) + bb.x;
+            v[4 * q + 0] = a > 0.f ? a : a * sl.x;
+            a = __uint_as_float(r[4 * q + 1]) + bb.y;
+            v[4 * q + 1] = a > 0.f ? a : a * sl.y;
+            a = __uint_as_float(r[4 * q + 2]) + bb.z;
+            v[4 * q + 2] = a > 0.f ? a : a * sl.z;
+            a = __uint_as_float(r[4 * q + 3]) + bb.w;
+            v[4 * q + 3] = a > 0.f ? a : a * sl.w;
+          }
+          if (out_kind == B200DN_OUT_NHWC16) {
+            if (is_bf16)
+              epilogue_nhwc16<true>(ea, v, out_pix, res_pix, t.n0 + c0);
+            else
+              epilogue_nhwc16<false>(ea, v, out_pix, res_pix, t.n0 + c0);
+          } else {
+            // fp32 NCHW output block: prelu(conv) + inputs   (UNet/RDUNet_model.py:186)
+            const int64_t hw = static_cast<int64_t>(H) * W;
+            const int64_t sp = static_cast<int64_t>(y) * W + x;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = t.n0 + c0 + j;
-            if (c < p.cout) {
-              float o = v[j];
-              if (p.res_nchw != nullptr)
-                o += __ldg(p.res_nchw + (static_cast<int64_t>(t.b % p.res_bmod) * p.cout + c) * hw + sp);
-              p.out_nchw[(static_cast<int64_t>(t.b) * p.cout + c) * hw + sp] = o;
+            for (int jj = 0; jj < 16; ++jj) {
+              const int c = t.n0 + c0 + jj;
+              if (c < cout) {
+                float o = v[jj];
+                if (res_nchw != nullptr)
+                  o += __ldg(res_nchw + (static_cast<int64_t>(t.b % res_bmod) * cout + c) * hw + sp);
+                out_nchw[(static_cast<int64_t>(t.b) * cout + c) * hw + sp] = o;
+              }
             }
           }
         }
@@ -402,12 +489,12 @@ cudaError_t g_attr_err = cudaSuccess;
 
 int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   B200DN_CHECK_ARG(a.mode >= 0 && a.mode <= 3, "igemm: bad mode %d", a.mode);
-  B200DN_CHECK_ARG(a.prec >= 0 && a.prec <= 3, "igemm: bad prec %d", a.prec);
+  B200DN_CHECK_ARG(a.prec >= 0 && a.prec <= 4, "igemm: bad prec %d", a.prec);
   B200DN_CHECK_ARG(a.B > 0 && a.H > 0 && a.W > 0 && a.cin > 0 && a.cout > 0, "igemm: non-positive dims");
   B200DN_CHECK_ARG(a.in[0] && a.wpacked && a.bias, "igemm: null input/weight/bias pointer");
   B200DN_CHECK_ARG(a.in_ctot % 8 == 0 && a.in_ctot >= a.cin, "igemm: in_ctot %d must be a multiple of 8 and >= cin %d",
                    a.in_ctot, a.cin);
-  const bool two_a = (a.prec == B200DN_PREC_BF16X2 || a.prec == B200DN_PREC_BF16X3);
+  const bool two_a = (a.prec == B200DN_PREC_BF16X2 || a.prec == B200DN_PREC_BF16X3 || a.prec == B200DN_PREC_FP16X2);
   const bool two_w = (a.prec == B200DN_PREC_BF16X3);
   B200DN_CHECK_ARG(!two_a || a.in[1], "igemm: prec %d needs the lo activation plane in[1]", a.prec);
   if (a.mode == B200DN_MODE_DOWN2X2)
@@ -417,10 +504,9 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
 
   KParams p;
   memset(&p, 0, sizeof(p));
-  p.mode = a.mode;
   p.taps = a.mode == B200DN_MODE_CONV3X3 ? 9 : a.mode == B200DN_MODE_DOWN2X2 ? 4 : 1;
   p.wgroups = a.mode == B200DN_MODE_CONV3X3 ? 9 : a.mode == B200DN_MODE_CONV1X1 ? 1 : 4;
-  p.n_groups = a.mode == B200DN_MODE_UP2X2 ? 4 : 1;
+  const int n_groups = a.mode == B200DN_MODE_UP2X2 ? 4 : 1;
   if (a.mode == B200DN_MODE_DOWN2X2) {
     p.B = 1;
     p.H = a.B * (a.H / 2);
@@ -430,7 +516,6 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     p.H = a.H;
     p.W = a.W;
   }
-  p.cin = a.cin;
   p.n_cblk = cdiv(a.cin, BLOCK_K);
   p.last_k16 = cdiv(a.cin - (p.n_cblk - 1) * BLOCK_K, 16);
   p.cout = a.cout;
@@ -444,14 +529,26 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   B200DN_CHECK_ARG(block_n % 16 == 0 && block_n >= 16 && block_n <= MAX_N, "igemm: block_n %d invalid", block_n);
   p.block_n = block_n;
   p.n_tiles_per_group = cdiv(cout_pad, block_n);
-  p.num_n_tiles = p.n_tiles_per_group * p.n_groups;
-  p.tiles_x = cdiv(p.W, TILE_W);
+  p.num_n_tiles = p.n_tiles_per_group * n_groups;
+  int sms = device_sm_count();
+  if (sms <= 0) return B200DN_E_CUDA;
+  // two x-adjacent A tiles per stage (M = 256 per W tile) when N is small enough for 4 accumulators in TMEM
+  // and there is enough work to keep every SM busy with the halved tile count
+  int mt = a.m_tiles;
+  B200DN_CHECK_ARG(mt >= 0 && mt <= 2, "igemm: m_tiles %d invalid", mt);
+  if (mt == 2) B200DN_CHECK_ARG(block_n <= 128, "igemm: m_tiles=2 needs block_n <= 128 (TMEM columns)");
+  if (mt == 0) {
+    const int64_t tiles2 = static_cast<int64_t>(p.B) * cdiv(p.W, 2 * TILE_W) * cdiv(p.H, TILE_H) * p.num_n_tiles;
+    mt = (block_n <= 128 && tiles2 >= 2 * sms) ? 2 : 1;
+  }
+  p.mt = mt;
+  p.tiles_x = cdiv(p.W, TILE_W * mt);
   p.tiles_y = cdiv(p.H, TILE_H);
-  p.num_m_tiles = p.B * p.tiles_x * p.tiles_y;
-  p.num_tiles = p.num_m_tiles * p.num_n_tiles;
-  p.fmt = (a.prec == B200DN_PREC_FP16) ? 0 : 1;
+  p.num_tiles = p.B * p.tiles_x * p.tiles_y * p.num_n_tiles;
+  p.fmt = (a.prec == B200DN_PREC_FP16 || a.prec == B200DN_PREC_FP16X2) ? 0 : 1;
   switch (a.prec) {
     case B200DN_PREC_BF16X2:
+    case B200DN_PREC_FP16X2:
       p.n_pairs = 2;
       p.pair_w[0] = 0, p.pair_a[0] = 1;  // small term first
       p.pair_w[1] = 0, p.pair_a[1] = 0;
@@ -466,11 +563,11 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
       p.n_pairs = 1;
       p.pair_w[0] = 0, p.pair_a[0] = 0;
   }
-  p.stage_bytes = A_BYTES + block_n * 128;
+  p.stage_bytes = mt * A_BYTES + block_n * 128;
   p.num_stages = RING_BYTES / p.stage_bytes;
   if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
   int cols = 32;
-  while (cols < 2 * block_n) cols <<= 1;
+  while (cols < 2 * mt * block_n) cols <<= 1;
   p.tmem_cols = cols;
 
   p.bias = a.bias;
@@ -538,16 +635,21 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
   }
 
+  using KernelFn = void (*)(KParams);
+  static const KernelFn kernels[3][2] = {{igemm_kernel<0, 1>, igemm_kernel<0, 2>},
+                                         {igemm_kernel<1, 1>, igemm_kernel<1, 2>},
+                                         {igemm_kernel<2, 1>, igemm_kernel<2, 2>}};
   std::call_once(g_attr_once, [] {
-    g_attr_err = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    for (int m = 0; m < 3 && g_attr_err == cudaSuccess; ++m)
+      for (int t = 0; t < 2 && g_attr_err == cudaSuccess; ++t)
+        g_attr_err = cudaFuncSetAttribute(kernels[m][t], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(igemm_kernel, smem)");
 
-  int sms = device_sm_count();
-  if (sms <= 0) return B200DN_E_CUDA;
   int grid = p.num_tiles < sms ? p.num_tiles : sms;
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
-  igemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  const int mode_idx = a.mode == B200DN_MODE_CONV3X3 ? 0 : a.mode == B200DN_MODE_DOWN2X2 ? 1 : 2;
+  kernels[mode_idx][mt - 1]<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   B200DN_CUDA(cudaGetLastError());
   return 0;
 }

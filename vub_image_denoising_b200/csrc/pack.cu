@@ -10,7 +10,7 @@ namespace b200dn {
 namespace {
 
 __device__ __forceinline__ uint16_t to16(float v, int prec) {
-  if (prec == B200DN_PREC_FP16) return __half_as_ushort(__float2half_rn(v));
+  if (prec == B200DN_PREC_FP16 || prec == B200DN_PREC_FP16X2) return __half_as_ushort(__float2half_rn(v));
   return __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 
@@ -41,7 +41,7 @@ __global__ void pack_kernel(const float* __restrict__ src, int cout, int cin, in
 int pack(const float* src, int cout, int cin, int groups, int prec, int transposed, void* packed, cudaStream_t stream) {
   B200DN_CHECK_ARG(src && packed, "pack: null pointer");
   B200DN_CHECK_ARG(cout > 0 && cin > 0 && groups > 0, "pack: non-positive dims");
-  B200DN_CHECK_ARG(prec >= 0 && prec <= 3, "pack: bad prec %d", prec);
+  B200DN_CHECK_ARG(prec >= 0 && prec <= 4, "pack: bad prec %d", prec);
   const int cin_pad = round_up(cin, 64), cout_pad = round_up(cout, 16);
   const int64_t n = static_cast<int64_t>(groups) * cout_pad * cin_pad;
   const int threads = 256;

@@ -277,7 +277,7 @@ class ForwardPlan:
         self.precision = precision
         self.B, self.H, self.W, self.F = B, H, W, F
         self.device = next(net.parameters()).device
-        self.two = self.prec in (_lib.PREC_BF16X2, _lib.PREC_BF16X3)
+        self.two = self.prec in _lib.TWO_PLANE_PRECS
         self.with_t = net._in_channels == net._img_channels + 1
         self.out_channels = net._out_channels
         self.signature = None
@@ -404,12 +404,14 @@ class ForwardPlan:
 
     # ---- execution
     def run(self, x: torch.Tensor, out: torch.Tensor, t: Optional[torch.Tensor] = None,
-            x_batch: Optional[int] = None, t_strides=None, t_ptr: Optional[int] = None) -> None:
+            x_batch: Optional[int] = None, t_strides=None, t_ptr: Optional[int] = None, events=None) -> None:
         """Enqueue one forward on the current stream.
 
         x: fp32 NCHW [Bx, 3, H, W] with Bx = x_batch or B; image b of the network batch reads x[b % Bx]
         (the sampler evaluates the same x_t at two timesteps as one 2B batch).  out: fp32 [B, 3, H, W].
         t: expanded [B, 1, H, W] view (strides are honoured), or (t_ptr, t_strides) raw.
+        events: optional (start, end) torch.cuda.Event pair recorded around the tensor-core launches
+        (after the ingest conv, after the last igemm) — bench.py's live per-kernel timing.
         """
         lib = self.lib
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -433,7 +435,11 @@ class ForwardPlan:
         oa.res_nchw = x.data_ptr()
         oa.res_bmod = bx
         igemm = lib.b200dn_igemm
+        if events is not None:
+            events[0].record()
         for ref in self._refs:
             rc = igemm(ref, stream)
             if rc:
                 _lib.check(rc, "igemm")
+        if events is not None:
+            events[1].record()
