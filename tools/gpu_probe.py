@@ -16,7 +16,7 @@ from helpers import effective_input, effective_weight, from_planes, to_planes, d
 DEV = "cuda"
 
 
-def conv_case(B, H, W, cin, cout, prec, mode=_lib.MODE_CONV3X3, block_n=0):
+def conv_case(B, H, W, cin, cout, prec, mode=_lib.MODE_CONV3X3, block_n=0, impl=0, mt=0):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(B, cin, H, W, generator=g).to(DEV)
     k = 3 if mode == _lib.MODE_CONV3X3 else 2
@@ -28,7 +28,7 @@ def conv_case(B, H, W, cin, cout, prec, mode=_lib.MODE_CONV3X3, block_n=0):
     Ho, Wo = (H, W) if mode == _lib.MODE_CONV3X3 else (H // 2, W // 2)
     out_hi = torch.zeros((B, Ho, Wo, cout), dtype=torch.int16, device=DEV)
     out_lo = torch.zeros_like(out_hi) if two_planes(prec) else None
-    torch.ops.b200dn.conv_igemm(x_hi, x_lo, wp, bias, slope, mode, prec, cin, cout, out_hi, out_lo, 0, None, None, block_n, 0)
+    torch.ops.b200dn.conv_igemm(x_hi, x_lo, wp, bias, slope, mode, prec, cin, cout, out_hi, out_lo, 0, None, None, block_n, 0, mt, impl)
     torch.cuda.synchronize()
     xe, we = effective_input(x, prec).double().cpu(), effective_weight(w, prec).double().cpu()
     ref = F.conv2d(xe, we, bias.double().cpu(), padding=1) if mode == _lib.MODE_CONV3X3 else F.conv2d(xe, we, bias.double().cpu(), stride=2)
@@ -36,7 +36,7 @@ def conv_case(B, H, W, cin, cout, prec, mode=_lib.MODE_CONV3X3, block_n=0):
     got = from_planes(out_hi, out_lo, prec, 0, cout).double().cpu()
     err = (got - ref).abs()
     rel = float(err.max() / ref.abs().max())
-    print(f"  mode {mode} prec {prec} B{B} {H}x{W} cin {cin} cout {cout} bn {block_n}: max err {float(err.max()):.3e} (rel {rel:.2e}), "
+    print(f"  mode {mode} impl {impl} mt {mt} prec {prec} B{B} {H}x{W} cin {cin} cout {cout} bn {block_n}: max err {float(err.max()):.3e} (rel {rel:.2e}), "
           f"ref absmax {float(ref.abs().max()):.3f}, got absmax {float(got.abs().max()):.3f}", flush=True)
     if rel > 0.02:
         # locate the damage: per-channel and per-position error maps
@@ -50,7 +50,7 @@ def conv_case(B, H, W, cin, cout, prec, mode=_lib.MODE_CONV3X3, block_n=0):
     return rel
 
 
-def bench_layer(B, H, W, cin, cout, prec=_lib.PREC_BF16, mode=_lib.MODE_CONV3X3, block_n=0, iters=10, res=False, mt=0):
+def bench_layer(B, H, W, cin, cout, prec=_lib.PREC_BF16, mode=_lib.MODE_CONV3X3, block_n=0, iters=10, res=False, mt=0, impl=0):
     d = dt16(prec)
     x_hi = (torch.randn(B, H, W, cin, device=DEV) * 0.5).to(d).view(torch.int16)
     x_lo = torch.zeros_like(x_hi) if two_planes(prec) else None
@@ -76,6 +76,7 @@ def bench_layer(B, H, W, cin, cout, prec=_lib.PREC_BF16, mode=_lib.MODE_CONV3X3,
         a.res_ctot = cin
     a.block_n = block_n
     a.m_tiles = mt
+    a.impl = impl
     L = _lib.lib()
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
@@ -90,8 +91,8 @@ def bench_layer(B, H, W, cin, cout, prec=_lib.PREC_BF16, mode=_lib.MODE_CONV3X3,
     ms = e0.elapsed_time(e1) / iters
     taps = 9 if mode == _lib.MODE_CONV3X3 else 4
     flops = 2.0 * B * Ho * Wo * taps * cin * cout
-    n_mma = {0: 1, 1: 1, 2: 2, 3: 3}[prec]
-    print(f"  bench B{B} {H}x{W} cin {cin:4d} cout {cout:4d} bn {block_n:3d} mt {mt} prec {prec}: {ms:8.3f} ms  "
+    n_mma = {0: 1, 1: 1, 2: 2, 3: 3, 4: 2}[prec]
+    print(f"  bench B{B} {H}x{W} cin {cin:4d} cout {cout:4d} bn {block_n:3d} mt {mt} impl {impl} prec {prec}: {ms:8.3f} ms  "
           f"{flops / ms / 1e9:8.1f} TFLOP/s (useful)  {flops * n_mma / ms / 1e9:8.1f} TFLOP/s (issued)", flush=True)
     return ms
 

@@ -43,7 +43,7 @@ class IgemmArgs(C.Structure):
         ("out", C.c_void_p * 2), ("out_ctot", C.c_int32), ("out_coff", C.c_int32),
         ("res", C.c_void_p * 2), ("res_ctot", C.c_int32),
         ("out_nchw", C.c_void_p), ("res_nchw", C.c_void_p), ("res_bmod", C.c_int32),
-        ("block_n", C.c_int32), ("max_ctas", C.c_int32), ("m_tiles", C.c_int32),
+        ("block_n", C.c_int32), ("max_ctas", C.c_int32), ("m_tiles", C.c_int32), ("impl", C.c_int32),
     ]
 
 

@@ -1,0 +1,277 @@
+// conv3x3_slab_sm100.cu — 3x3 / stride 1 / pad 1 convolution as a tcgen05 implicit GEMM that loads every input
+// pixel into shared memory ONCE per 64-channel block instead of once per filter tap.
+//
+// Reference op: nn.Conv2d(.,.,3,padding=1) + nn.PReLU (+ dense-block residual / output-block residual),
+// UNet/RDUNet_model.py:61,74-75,86-87,98-115,186 — 63 of the network's 69 convolutions, 97.5 % of its FLOPs.
+//
+// Why: the per-tap kernel (igemm_sm100.cu) is bound by shared-memory bandwidth — every pipeline stage writes
+// an A tile (TMA) that is read by only four UMMAs, and TMA writes + UMMA operand reads share ~128 B/clk/SM.
+// Here one TMA box brings a haloed slab [ (16*MT+2) rows x 16 px x 64 ch ] (zero-filled outside the image =
+// the conv's padding); the 9 taps are 9 UMMA descriptors into that slab, shifted by (dy*16 + dx) rows of 128 B.
+// The slab pitch is 16 pixels, so the 8-row core-matrix groups of a tap sit 2048 B apart (SBO).  Measured on
+// B200 (tools/slab_probe.py): the 128B-swizzle XOR of both TMA and UMMA is a function of the ABSOLUTE shared
+// memory address bits [7,10), so a descriptor whose start address is shifted by whole 128 B rows reads the
+// TMA-written slab correctly with the descriptor's base-offset field left at 0 (setting it to
+// (addr >> 7) & 7 produces garbage).
+// A-side smem write traffic drops 4x, A TMA instructions 9x, L2->SM traffic ~4x.
+//
+// Warp roles: 0 = slab TMA producer, 2 = TMEM allocator then W-tile TMA producer (one [N x 64] tile per tap),
+// 1 / 3 = MMA issuers of sub-tile 0 / 1 (MT = 2 stacks two 8x16-pixel tiles vertically), 4..7 = epilogue.
+#include "igemm_common.cuh"
+
+#include <mutex>
+
+namespace b200dn {
+namespace igemm {
+
+namespace {
+
+constexpr int TW = SLAB_TILE_W;   // 8
+constexpr int TH = SLAB_TILE_H;   // 16
+constexpr int MAX_SLABS = 3;
+constexpr int SMEM_BYTES_SLAB = 1024 + SLAB_DATA_BYTES + 256 + 2 * 2 * MAX_N * 4;
+
+// barrier map (byte offsets from `bars`)
+constexpr uint32_t B_SLAB_FULL = 0, B_SLAB_EMPTY = 24, B_W_FULL = 48, B_W_EMPTY = 112, B_TFULL = 176, B_TEMPTY = 192,
+                   B_TMEM_PTR = 208;
+
+__device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_off) {
+  return make_sw128_desc(smem_addr, sbo_bytes) | (static_cast<uint64_t>(base_off & 7u) << 49);
+}
+
+template <int MT>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
+  const uint32_t bars = smem_base + SLAB_DATA_BYTES;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + SLAB_DATA_BYTES + B_TMEM_PTR);
+  float* epi_bias = reinterpret_cast<float*>(smem_gen + SLAB_DATA_BYTES + 256);  // [2][MAX_N]
+  float* epi_slope = epi_bias + 2 * MAX_N;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmW);
+    if (p.n_pairs > 1) tma_prefetch_desc(&p.tmA1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < MAX_SLABS; ++s) {
+      mbar_init(bars + B_SLAB_FULL + s * 8, 1);
+      mbar_init(bars + B_SLAB_EMPTY + s * 8, MT);
+    }
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(bars + B_W_FULL + s * 8, 1);
+      mbar_init(bars + B_W_EMPTY + s * 8, MT);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bars + B_TFULL + a * 8, MT);
+      mbar_init(bars + B_TEMPTY + a * 8, EPI_THREADS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_ptr_s), static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int num_tiles = p.num_tiles, grid = gridDim.x;
+  const int num_n_tiles = p.num_n_tiles, n_tiles_per_group = p.n_tiles_per_group, block_n = p.block_n;
+  const int tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+  const int n_cblk = p.n_cblk, n_pairs = p.n_pairs;
+  const int num_slabs = p.num_slabs, slab_bytes = p.slab_bytes;
+  const int num_stages = p.num_stages, stage_bytes = p.stage_bytes;
+  const uint32_t wring = smem_base + static_cast<uint32_t>(num_slabs * slab_bytes);
+  constexpr int STH = TH * MT;
+
+  if (warp == 0) {
+    // ===================================================== slab TMA producer: one box per (pair, 64-channel block)
+    int s = 0;
+    uint32_t sph = 0;
+    const int pa0 = p.pair_a[0], pa1 = p.pair_a[1], pa2 = p.pair_a[2];
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
+      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
+      for (int pair = 0; pair < n_pairs; ++pair) {
+        const int pa = pair == 0 ? pa0 : pair == 1 ? pa1 : pa2;
+        const CUtensorMap* tmA = pa ? &p.tmA1 : &p.tmA0;
+        for (int cb = 0; cb < n_cblk; ++cb) {
+          mbar_wait(bars + B_SLAB_EMPTY + s * 8, sph ^ 1u);
+          if (elect_one()) {
+            const uint32_t full = bars + B_SLAB_FULL + s * 8;
+            mbar_arrive_expect_tx(full, static_cast<uint32_t>(slab_bytes));
+            tma_load_4d(smem_base + s * slab_bytes, tmA, full, cb * BLOCK_K, t.x0 - 1, t.y0 - 1, t.b);
+          }
+          __syncwarp();
+          if (++s == num_slabs) {
+            s = 0;
+            sph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================== W-tile TMA producer: one [N x 64] tile per tap
+    int ws = 0;
+    uint32_t wph = 0;
+    const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128);
+    const int pw0 = p.pair_w[0] * 9, pw1 = p.pair_w[1] * 9, pw2 = p.pair_w[2] * 9;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
+      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
+      for (int pair = 0; pair < n_pairs; ++pair) {
+        const int wbase = pair == 0 ? pw0 : pair == 1 ? pw1 : pw2;
+        for (int cb = 0; cb < n_cblk; ++cb) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bars + B_W_EMPTY + ws * 8, wph ^ 1u);
+            if (elect_one()) {
+              const uint32_t full = bars + B_W_FULL + ws * 8;
+              mbar_arrive_expect_tx(full, w_bytes);
+              tma_load_3d(wring + ws * stage_bytes, &p.tmW, full, cb * BLOCK_K, t.n0, wbase + tap);
+            }
+            __syncwarp();
+            if (++ws == num_stages) {
+              ws = 0;
+              wph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || (warp == 3 && MT == 2)) {
+    // ===================================================== MMA issuer of sub-tile j
+    const int j = warp == 1 ? 0 : 1;
+    const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.fmt), static_cast<uint32_t>(block_n));
+    const int kc_iters = n_pairs * n_cblk;
+    const int last_k16 = p.last_k16;
+    const uint32_t pitch = static_cast<uint32_t>(p.slab_w * 128);   // bytes per slab pixel row = SBO
+    const uint32_t bo_mode = static_cast<uint32_t>(p.bo_mode);
+    int s = 0, ws = 0;
+    uint32_t sph = 0, wph = 0;
+    int local_tile = 0;
+    uint32_t ready = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = (local_tile >> 1) & 1;
+      mbar_wait(bars + B_TEMPTY + acc * 8, acc_phase ^ 1u);
+      const uint32_t d = tmem_base + static_cast<uint32_t>((acc * MT + j) * block_n);
+      uint32_t accumulate = 0;
+      int cb = 0;
+      for (int kc = 0; kc < kc_iters; ++kc) {
+        const bool full_block = (cb != n_cblk - 1) || (last_k16 == BLOCK_K / 16);
+        mbar_wait(bars + B_SLAB_FULL + s * 8, sph);
+        const uint32_t slab = smem_base + static_cast<uint32_t>(s * slab_bytes) + static_cast<uint32_t>(j * TH) * pitch;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap % 3;
+          if (!ready) mbar_wait(bars + B_W_FULL + ws * 8, wph);
+          tc_fence_after();
+          const uint32_t w_addr = wring + ws * stage_bytes;
+          const uint32_t w_empty = bars + B_W_EMPTY + ws * 8;
+          if (++ws == num_stages) {
+            ws = 0;
+            wph ^= 1u;
+          }
+          ready = mbar_test_wait(bars + B_W_FULL + ws * 8, wph);   // peek at the next W tile
+          if (elect_one()) {
+            const uint32_t a_addr = slab + static_cast<uint32_t>(dy) * pitch + static_cast<uint32_t>(dx * 128);
+            const uint64_t adesc = make_sw128_desc_bo(a_addr, pitch, bo_mode ? (a_addr >> 7) : 0u);
+            const uint64_t bdesc = make_sw128_desc(w_addr, 1024);
+            if (full_block) {
+              umma_f16(d, adesc, bdesc, idesc, accumulate);
+              umma_f16(d, adesc + 2, bdesc + 2, idesc, 1u);
+              umma_f16(d, adesc + 4, bdesc + 4, idesc, 1u);
+              umma_f16(d, adesc + 6, bdesc + 6, idesc, 1u);
+            } else {
+              for (int k = 0; k < last_k16; ++k)
+                umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? accumulate : 1u);
+            }
+            umma_commit(w_empty);
+            if (tap == 8) {
+              umma_commit(bars + B_SLAB_EMPTY + s * 8);                         // slab consumed by all 9 taps
+              if (kc == kc_iters - 1) umma_commit(bars + B_TFULL + acc * 8);    // accumulator complete
+            }
+          }
+          __syncwarp();
+          accumulate = 1;
+        }
+        if (++s == num_slabs) {
+          s = 0;
+          sph ^= 1u;
+        }
+        if (++cb == n_cblk) cb = 0;
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================================= epilogue
+    const int we = warp & 3;
+    const int row = we * 32 + lane;
+    const int th = row / TW, tw = row - th * TW;
+    const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);
+    const EpiArgs ea = make_epi_args(p);
+    const int H = p.H, W = p.W, cout = p.cout;
+    const float* bias = p.bias;
+    const float* slope = p.slope;
+    int local_tile = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
+      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = (local_tile >> 1) & 1;
+      float* bs = epi_bias + acc * MAX_N;
+      float* ss = epi_slope + acc * MAX_N;
+      stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et);
+
+      mbar_wait(bars + B_TFULL + acc * 8, acc_phase);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+        const int y = t.y0 + j * TH + th, x = t.x0 + tw;
+        const bool valid = (y < H) && (x < W);
+        const int64_t pix = (static_cast<int64_t>(t.b) * H + y) * W + x;
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n);
+        epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, pix, pix, t.n0,
+                         j == MT - 1 ? bars + B_TEMPTY + acc * 8 : 0u);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+std::once_flag g_once;
+cudaError_t g_err = cudaSuccess;
+
+}  // namespace
+
+int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream) {
+  B200DN_CHECK_ARG(p.num_stages >= 2, "conv3x3 slab: W ring too small for block_n %d", p.block_n);
+  B200DN_CHECK_ARG(p.num_slabs <= MAX_SLABS, "conv3x3 slab: too many slabs");
+  std::call_once(g_once, [] {
+    g_err = cudaFuncSetAttribute(conv3x3_slab_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB);
+    if (g_err == cudaSuccess)
+      g_err = cudaFuncSetAttribute(conv3x3_slab_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB);
+  });
+  if (g_err != cudaSuccess) return cuda_fail(g_err, "cudaFuncSetAttribute(conv3x3_slab_kernel, smem)");
+  if (p.mt == 2)
+    conv3x3_slab_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES_SLAB, stream>>>(p);
+  else
+    conv3x3_slab_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES_SLAB, stream>>>(p);
+  B200DN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace igemm
+}  // namespace b200dn

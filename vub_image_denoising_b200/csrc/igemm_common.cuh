@@ -1,0 +1,229 @@
+// igemm_common.cuh — pieces shared by the two tensor-core convolution kernels:
+//   igemm_sm100.cu          per-tap A-tile reload; all modes (3x3, 2x2 stride 2, transposed 2x2, 1x1)
+//   conv3x3_slab_sm100.cu   3x3 only; one haloed input slab per 64-channel block, 9 shifted UMMA descriptors
+// Both write through the same fused epilogue (bias + PReLU + residual + channel-slice store).
+#pragma once
+#include "common.cuh"
+
+namespace b200dn {
+namespace igemm {
+
+constexpr int BLOCK_M = 128;  // UMMA M (pixels per accumulator)
+constexpr int BLOCK_K = 64;   // 64 x 16-bit = one 128-byte swizzle row
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int MAX_N = 256;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+constexpr int MAX_STAGES = 8;
+
+struct __align__(64) KParams {
+  CUtensorMap tmA0, tmA1, tmW;
+  int taps;
+  int B, H, W;  // GEMM-M domain (pixels the accumulator rows enumerate)
+  int n_cblk, last_k16;
+  int cout, block_n;
+  int mt;       // A tiles (128 pixels each) sharing one W tile
+  int n_tiles_per_group, num_n_tiles;
+  int tiles_x, tiles_y, num_tiles;   // spatial tiling in super tiles (mt sub-tiles each)
+  int n_pairs, pair_a[3], pair_w[3];
+  int wgroups;
+  int fmt;  // 1 bf16, 0 fp16
+  int num_stages, stage_bytes, tmem_cols;
+  // slab kernel only
+  int slab_w, slab_bytes, num_slabs, bo_mode;
+  const float* bias;
+  const float* slope;
+  int out_kind;
+  void* out0;
+  void* out1;
+  int out_ctot, out_coff;
+  const void* res0;
+  const void* res1;
+  int res_ctot;
+  float* out_nchw;
+  const float* res_nchw;
+  int res_bmod;
+};
+
+struct TileCoord {
+  int b, y0, x0, grp, n0;
+};
+
+// tile -> (image, super-tile origin, N group, N offset); super tile = tile_w x tile_h pixels
+__device__ __forceinline__ TileCoord decode_tile(int tile, int num_n_tiles, int n_tiles_per_group, int block_n,
+                                                 int tiles_x, int tiles_y, int tile_w, int tile_h) {
+  TileCoord t;
+  const int m_tile = tile / num_n_tiles;
+  const int nt = tile - m_tile * num_n_tiles;
+  t.grp = nt / n_tiles_per_group;
+  t.n0 = (nt - t.grp * n_tiles_per_group) * block_n;
+  const int per_img = tiles_x * tiles_y;
+  t.b = m_tile / per_img;
+  const int r = m_tile - t.b * per_img;
+  const int ty = r / tiles_x;
+  t.y0 = ty * tile_h;
+  t.x0 = (r - ty * tiles_x) * tile_w;
+  return t;
+}
+
+template <bool kBf16>
+__device__ __forceinline__ float cvt_lo(uint32_t v) {
+  return kBf16 ? bf16_lo(v) : f16_lo(v);
+}
+template <bool kBf16>
+__device__ __forceinline__ float cvt_hi(uint32_t v) {
+  return kBf16 ? bf16_hi(v) : f16_hi(v);
+}
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (kBf16) return pack_bf16x2(a, b);
+  // fp16 storage saturates instead of overflowing to inf
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  return pack_f16x2(a, b);
+}
+
+struct EpiArgs {
+  void* out0;
+  void* out1;
+  const void* res0;
+  const void* res1;
+  int out_ctot, out_coff, res_ctot, cout;
+  int out_kind, is_bf16;
+  float* out_nchw;
+  const float* res_nchw;
+  int res_bmod, H, W;
+};
+
+__device__ __forceinline__ EpiArgs make_epi_args(const KParams& p) {
+  EpiArgs e;
+  e.out0 = p.out0, e.out1 = p.out1, e.res0 = p.res0, e.res1 = p.res1;
+  e.out_ctot = p.out_ctot, e.out_coff = p.out_coff, e.res_ctot = p.res_ctot, e.cout = p.cout;
+  e.out_kind = p.out_kind, e.is_bf16 = p.fmt != 0;
+  e.out_nchw = p.out_nchw, e.res_nchw = p.res_nchw, e.res_bmod = p.res_bmod, e.H = p.H, e.W = p.W;
+  return e;
+}
+
+// 16 accumulator columns of one pixel -> 16 channels of the NHWC slice.
+template <bool kBf16>
+__device__ __forceinline__ void epilogue_nhwc16(const EpiArgs& e, float (&v)[16], int64_t out_pix, int64_t res_pix,
+                                                int ch0) {
+  if (ch0 >= e.cout) return;
+  const bool half1 = (ch0 + 8) < e.cout;  // second 8-channel group inside cout
+  if (e.res0 != nullptr) {
+    const uint4* r0 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(e.res0) + res_pix * e.res_ctot + ch0);
+    uint4 q[2];
+    q[0] = __ldg(r0);
+    q[1] = half1 ? __ldg(r0 + 1) : make_uint4(0, 0, 0, 0);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(q);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[2 * j] += cvt_lo<kBf16>(w[j]);
+      v[2 * j + 1] += cvt_hi<kBf16>(w[j]);
+    }
+    if (e.res1 != nullptr) {
+      const uint4* r1 =
+          reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(e.res1) + res_pix * e.res_ctot + ch0);
+      q[0] = __ldg(r1);
+      q[1] = half1 ? __ldg(r1 + 1) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[2 * j] += cvt_lo<kBf16>(w[j]);
+        v[2 * j + 1] += cvt_hi<kBf16>(w[j]);
+      }
+    }
+  }
+  uint32_t hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hi[j] = pack2<kBf16>(v[2 * j], v[2 * j + 1]);
+  uint4* o0 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(e.out0) + out_pix * e.out_ctot + e.out_coff + ch0);
+  o0[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (half1) o0[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  if (e.out1 != nullptr) {
+    uint32_t lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = v[2 * j] - cvt_lo<kBf16>(hi[j]);
+      const float b = v[2 * j + 1] - cvt_hi<kBf16>(hi[j]);
+      lo[j] = pack2<kBf16>(a, b);
+    }
+    uint4* o1 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(e.out1) + out_pix * e.out_ctot + e.out_coff + ch0);
+    o1[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (half1) o1[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+}
+
+// Drain one 128 x block_n accumulator (this thread = one pixel row): TMEM -> +bias -> PReLU -> (+residual) -> store.
+// `release_bar` != 0: arrive on it right after the last TMEM read (hands the accumulator stage back to the MMA warps).
+__device__ __forceinline__ void epilogue_subtile(const EpiArgs& e, uint32_t taddr, int block_n, const float* bs,
+                                                 const float* ss, bool valid, int b, int y, int x, int64_t out_pix,
+                                                 int64_t res_pix, int n0, uint32_t release_bar) {
+  for (int c0 = 0; c0 < block_n; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + c0, r);
+    tmem_ld_wait();
+    if (release_bar != 0 && c0 + 16 >= block_n) {
+      tc_fence_before();
+      mbar_arrive(release_bar);
+    }
+    if (!valid) continue;
+    float v[16];
+    const float4* b4 = reinterpret_cast<const float4*>(bs + c0);
+    const float4* s4 = reinterpret_cast<const float4*>(ss + c0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bb = b4[q];
+      const float4 sl = s4[q];
+      float a;
+      a = __uint_as_float(r[4 * q + 0]) + bb.x;
+      v[4 * q + 0] = a > 0.f ? a : a * sl.x;
+      a = __uint_as_float(r[4 * q + 1]) + bb.y;
+      v[4 * q + 1] = a > 0.f ? a : a * sl.y;
+      a = __uint_as_float(r[4 * q + 2]) + bb.z;
+      v[4 * q + 2] = a > 0.f ? a : a * sl.z;
+      a = __uint_as_float(r[4 * q + 3]) + bb.w;
+      v[4 * q + 3] = a > 0.f ? a : a * sl.w;
+    }
+    if (e.out_kind == B200DN_OUT_NHWC16) {
+      if (e.is_bf16)
+        epilogue_nhwc16<true>(e, v, out_pix, res_pix, n0 + c0);
+      else
+        epilogue_nhwc16<false>(e, v, out_pix, res_pix, n0 + c0);
+    } else {
+      // fp32 NCHW output block: prelu(conv) + inputs   (UNet/RDUNet_model.py:186)
+      const int64_t hw = static_cast<int64_t>(e.H) * e.W;
+      const int64_t sp = static_cast<int64_t>(y) * e.W + x;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const int c = n0 + c0 + jj;
+        if (c < e.cout) {
+          float o = v[jj];
+          if (e.res_nchw != nullptr)
+            o += __ldg(e.res_nchw + (static_cast<int64_t>(b % e.res_bmod) * e.cout + c) * hw + sp);
+          e.out_nchw[(static_cast<int64_t>(b) * e.cout + c) * hw + sp] = o;
+        }
+      }
+    }
+  }
+}
+
+// stage the tile's bias / PReLU slopes in shared memory (called by the 128 epilogue threads)
+__device__ __forceinline__ void stage_bias_slope(float* bs, float* ss, const float* bias, const float* slope, int n0,
+                                                 int block_n, int cout, int et) {
+  for (int i = et; i < block_n; i += EPI_THREADS) {
+    const int c = n0 + i;
+    bs[i] = (c < cout) ? __ldg(bias + c) : 0.f;
+    ss[i] = (slope != nullptr && c < cout) ? __ldg(slope + c) : 1.f;
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+}
+
+// slab-kernel launcher (conv3x3_slab_sm100.cu); p is fully populated by igemm_launch
+int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream);
+// shared-memory budget of the slab kernel, used by the host to size the rings
+constexpr int SLAB_DATA_BYTES = 208 * 1024;
+constexpr int SLAB_TILE_W = 8;    // output tile: 8 wide x 16 tall pixels per accumulator
+constexpr int SLAB_TILE_H = 16;
+
+}  // namespace igemm
+}  // namespace b200dn

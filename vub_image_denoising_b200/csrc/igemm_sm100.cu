@@ -20,151 +20,30 @@
 //   warp 2          : TMEM allocator.
 //   warps 4..7      : epilogue.  tcgen05.ld -> +bias -> PReLU -> (+residual) -> 16-bit planes into the
 //                     NHWC channel slice, or fp32 NCHW (+fp32 NCHW residual) for the output block.
-#include "common.cuh"
+#include "igemm_common.cuh"
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef B200DN_DEFAULT_CONV3X3_IMPL
+#define B200DN_DEFAULT_CONV3X3_IMPL 2
+#endif
 
 namespace b200dn {
 
+using namespace igemm;
+
 namespace {
 
-constexpr int TILE_W = 16;
+constexpr int TILE_W = 16;   // accumulator tile of the tap-reload kernel: 16 wide x 8 tall pixels
 constexpr int TILE_H = 8;
-constexpr int BLOCK_M = TILE_W * TILE_H;  // 128 = UMMA M
-constexpr int BLOCK_K = 64;               // 64 x 16-bit = one 128-byte swizzle row
-constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int RING_BYTES = 192 * 1024;
-constexpr int MAX_STAGES = 8;
-constexpr int MAX_N = 256;
-constexpr int MISC_BYTES = 256 + 4 * MAX_N * 4 * 1;  // barriers + tmem ptr, then bias/slope [2][256] each
 constexpr int SMEM_BYTES = 1024 + RING_BYTES + 256 + 2 * 2 * MAX_N * 4;
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_THREADS = 128;
-
-struct __align__(64) KParams {
-  CUtensorMap tmA0, tmA1, tmW;
-  int taps;
-  int B, H, W;  // GEMM-M domain (pixels the accumulator rows enumerate)
-  int n_cblk, last_k16;
-  int cout, block_n;
-  int mt;       // A tiles (128 pixels each, x-adjacent) sharing one W tile per pipeline stage: 1 or 2
-  int n_tiles_per_group, num_n_tiles;
-  int tiles_x, tiles_y, num_tiles;   // tiles_x counts super tiles (mt * 16 pixels wide)
-  int n_pairs, pair_a[3], pair_w[3];
-  int wgroups;
-  int fmt;  // 1 bf16, 0 fp16
-  int num_stages, stage_bytes, tmem_cols;
-  const float* bias;
-  const float* slope;
-  int out_kind;
-  void* out0;
-  void* out1;
-  int out_ctot, out_coff;
-  const void* res0;
-  const void* res1;
-  int res_ctot;
-  float* out_nchw;
-  const float* res_nchw;
-  int res_bmod;
-};
-
-struct TileCoord {
-  int b, y0, x0, grp, n0;
-};
-
-__device__ __forceinline__ TileCoord decode_tile(int tile, int num_n_tiles, int n_tiles_per_group, int block_n,
-                                                 int tiles_x, int tiles_y, int mt) {
-  TileCoord t;
-  const int m_tile = tile / num_n_tiles;
-  const int nt = tile - m_tile * num_n_tiles;
-  t.grp = nt / n_tiles_per_group;
-  t.n0 = (nt - t.grp * n_tiles_per_group) * block_n;
-  const int per_img = tiles_x * tiles_y;
-  t.b = m_tile / per_img;
-  const int r = m_tile - t.b * per_img;
-  const int ty = r / tiles_x;
-  t.y0 = ty * TILE_H;
-  t.x0 = (r - ty * tiles_x) * (TILE_W * mt);
-  return t;
-}
-
-template <bool kBf16>
-__device__ __forceinline__ float cvt_lo(uint32_t v) {
-  return kBf16 ? bf16_lo(v) : f16_lo(v);
-}
-template <bool kBf16>
-__device__ __forceinline__ float cvt_hi(uint32_t v) {
-  return kBf16 ? bf16_hi(v) : f16_hi(v);
-}
-template <bool kBf16>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if (kBf16) return pack_bf16x2(a, b);
-  // fp16 storage saturates instead of overflowing to inf
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  return pack_f16x2(a, b);
-}
-
-struct EpiArgs {
-  void* out0;
-  void* out1;
-  const void* res0;
-  const void* res1;
-  int out_ctot, out_coff, res_ctot, cout;
-};
-
-// 16 accumulator columns of one pixel -> 16 channels of the NHWC slice.
-template <bool kBf16>
-__device__ __forceinline__ void epilogue_nhwc16(const EpiArgs& e, float (&v)[16], int64_t out_pix, int64_t res_pix,
-                                                int ch0) {
-  if (ch0 >= e.cout) return;
-  const bool half1 = (ch0 + 8) < e.cout;  // second 8-channel group inside cout
-  if (e.res0 != nullptr) {
-    const uint4* r0 = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(e.res0) + res_pix * e.res_ctot + ch0);
-    uint4 q[2];
-    q[0] = __ldg(r0);
-    q[1] = half1 ? __ldg(r0 + 1) : make_uint4(0, 0, 0, 0);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(q);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[2 * j] += cvt_lo<kBf16>(w[j]);
-      v[2 * j + 1] += cvt_hi<kBf16>(w[j]);
-    }
-    if (e.res1 != nullptr) {
-      const uint4* r1 =
-          reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(e.res1) + res_pix * e.res_ctot + ch0);
-      q[0] = __ldg(r1);
-      q[1] = half1 ? __ldg(r1 + 1) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[2 * j] += cvt_lo<kBf16>(w[j]);
-        v[2 * j + 1] += cvt_hi<kBf16>(w[j]);
-      }
-    }
-  }
-  uint32_t hi[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) hi[j] = pack2<kBf16>(v[2 * j], v[2 * j + 1]);
-  uint4* o0 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(e.out0) + out_pix * e.out_ctot + e.out_coff + ch0);
-  o0[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  if (half1) o0[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-  if (e.out1 != nullptr) {
-    uint32_t lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float a = v[2 * j] - cvt_lo<kBf16>(hi[j]);
-      const float b = v[2 * j + 1] - cvt_hi<kBf16>(hi[j]);
-      lo[j] = pack2<kBf16>(a, b);
-    }
-    uint4* o1 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(e.out1) + out_pix * e.out_ctot + e.out_coff + ch0);
-    o1[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    if (half1) o1[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-  }
-}
 
 // MODE: 0 = CONV3X3 (9 taps, shifted 4-D boxes), 1 = DOWN2X2 (4 taps, 5-D map), 2 = UP2X2 / CONV1X1 (one tap)
-// MT:   A tiles (128 pixels each) per W tile and pipeline stage.
+// MT:   A tiles (128 pixels each, x-adjacent) per W tile and pipeline stage.
 //
 // Warp roles (256 threads): 0 = A-tile TMA producer, 2 = TMEM allocator then W-tile TMA producer,
 // 1 = MMA issuer of sub-tile 0, 3 = MMA issuer of sub-tile 1 (MT == 2), 4..7 = epilogue.
@@ -220,6 +99,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   constexpr int KY = MODE == 0 ? 3 : MODE == 1 ? 2 : 1;
   constexpr int KX = KY;
   constexpr uint32_t W_OFF = MT * A_BYTES;
+  constexpr int STW = TILE_W * MT;   // super-tile width
 
   if (warp == 0) {
     // ===================================================== A-tile TMA producer
@@ -227,7 +107,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     uint32_t phase = 0;
     const int pa0 = p.pair_a[0], pa1 = p.pair_a[1], pa2 = p.pair_a[2];
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
-      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, MT);
+      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int pa = pair == 0 ? pa0 : pair == 1 ? pa1 : pa2;
         const CUtensorMap* tmA = pa ? &p.tmA1 : &p.tmA0;
@@ -270,7 +150,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     const int wg = p.wgroups;
     const int pw0 = p.pair_w[0] * wg, pw1 = p.pair_w[1] * wg, pw2 = p.pair_w[2] * wg;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
-      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, MT);
+      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int wbase = pair == 0 ? pw0 : pair == 1 ? pw1 : pw2;
 #pragma unroll
@@ -347,30 +227,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     const int row = we * 32 + lane;
     const int th = row / TILE_W, tw = row - th * TILE_W;
     const int et = threadIdx.x - (NUM_THREADS - EPI_THREADS);
-    const bool is_bf16 = p.fmt != 0;
-    const int H = p.H, W = p.W, cout = p.cout, out_kind = p.out_kind;
+    const EpiArgs ea = make_epi_args(p);
+    const int H = p.H, W = p.W, cout = p.cout;
     const float* bias = p.bias;
     const float* slope = p.slope;
-    EpiArgs ea;
-    ea.out0 = p.out0, ea.out1 = p.out1, ea.res0 = p.res0, ea.res1 = p.res1;
-    ea.out_ctot = p.out_ctot, ea.out_coff = p.out_coff, ea.res_ctot = p.res_ctot, ea.cout = cout;
-    float* out_nchw = p.out_nchw;
-    const float* res_nchw = p.res_nchw;
-    const int res_bmod = p.res_bmod;
     const bool up = p.wgroups == 4 && MODE == 2;
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
-      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, MT);
+      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (local_tile >> 1) & 1;
       float* bs = epi_bias + acc * MAX_N;
       float* ss = epi_slope + acc * MAX_N;
-      for (int i = et; i < block_n; i += EPI_THREADS) {
-        const int c = t.n0 + i;
-        bs[i] = (c < cout) ? __ldg(bias + c) : 0.f;
-        ss[i] = (slope != nullptr && c < cout) ? __ldg(slope + c) : 1.f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+      stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et);
 
       mbar_wait(bars + 128 + acc * 8, acc_phase);
       tc_fence_after();
@@ -387,54 +256,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         }
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n);
-        for (int c0 = 0; c0 < block_n; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c0, r);
-          tmem_ld_wait();
-          if (j == MT - 1 && c0 + 16 >= block_n) {
-            // all TMEM reads of this accumulator stage are done: hand it back to the MMA warps
-            tc_fence_before();
-            mbar_arrive(bars + 144 + acc * 8);
-          }
-          if (!valid) continue;
-          float v[16];
-          const float4* b4 = reinterpret_cast<const float4*>(bs + c0);
-          const float4* s4 = reinterpret_cast<const float4*>(ss + c0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 bb = b4[q];
-            const float4 sl = s4[q];
-            float a;
-            a = __uint_as_float(r[4 * q + 0]) + bb.x;
-            v[4 * q + 0] = a > 0.f ? a : a * sl.x;
-            a = __uint_as_float(r[4 * q + 1]) + bb.y;
-            v[4 * q + 1] = a > 0.f ? a : a * sl.y;
-            a = __uint_as_float(r[4 * q + 2]) + bb.z;
-            v[4 * q + 2] = a > 0.f ? a : a * sl.z;
-            a = __uint_as_float(r[4 * q + 3]) + bb.w;
-            v[4 * q + 3] = a > 0.f ? a : a * sl.w;
-          }
-          if (out_kind == B200DN_OUT_NHWC16) {
-            if (is_bf16)
-              epilogue_nhwc16<true>(ea, v, out_pix, res_pix, t.n0 + c0);
-            else
-              epilogue_nhwc16<false>(ea, v, out_pix, res_pix, t.n0 + c0);
-          } else {
-            // fp32 NCHW output block: prelu(conv) + inputs   (UNet/RDUNet_model.py:186)
-            const int64_t hw = static_cast<int64_t>(H) * W;
-            const int64_t sp = static_cast<int64_t>(y) * W + x;
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int c = t.n0 + c0 + jj;
-              if (c < cout) {
-                float o = v[jj];
-                if (res_nchw != nullptr)
-                  o += __ldg(res_nchw + (static_cast<int64_t>(t.b % res_bmod) * cout + c) * hw + sp);
-                out_nchw[(static_cast<int64_t>(t.b) * cout + c) * hw + sp] = o;
-              }
-            }
-          }
-        }
+        epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, out_pix, res_pix, t.n0,
+                         j == MT - 1 ? bars + 144 + acc * 8 : 0u);
       }
     }
   }
@@ -485,6 +308,25 @@ int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, 
 std::once_flag g_attr_once;
 cudaError_t g_attr_err = cudaSuccess;
 
+// default conv3x3 implementation: 1 = per-tap reload (this file), 2 = haloed slab (conv3x3_slab_sm100.cu);
+// B200DN_CONV3X3_IMPL=tap|slab overrides, b200dn_igemm_args.impl overrides both.
+int default_conv3x3_impl() {
+  static int impl = [] {
+    const char* e = getenv("B200DN_CONV3X3_IMPL");
+    if (e && !strcmp(e, "tap")) return 1;
+    if (e && !strcmp(e, "slab")) return 2;
+    return B200DN_DEFAULT_CONV3X3_IMPL;
+  }();
+  return impl;
+}
+int slab_bo_mode() {
+  static int mode = [] {
+    const char* e = getenv("B200DN_SLAB_BO");
+    return e ? atoi(e) : 0;   // measured on B200: the swizzle XOR uses absolute smem address bits, base offset stays 0
+  }();
+  return mode;
+}
+
 }  // namespace
 
 int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
@@ -494,6 +336,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   B200DN_CHECK_ARG(a.in[0] && a.wpacked && a.bias, "igemm: null input/weight/bias pointer");
   B200DN_CHECK_ARG(a.in_ctot % 8 == 0 && a.in_ctot >= a.cin, "igemm: in_ctot %d must be a multiple of 8 and >= cin %d",
                    a.in_ctot, a.cin);
+  B200DN_CHECK_ARG(a.impl >= 0 && a.impl <= 2, "igemm: bad impl %d", a.impl);
   const bool two_a = (a.prec == B200DN_PREC_BF16X2 || a.prec == B200DN_PREC_BF16X3 || a.prec == B200DN_PREC_FP16X2);
   const bool two_w = (a.prec == B200DN_PREC_BF16X3);
   B200DN_CHECK_ARG(!two_a || a.in[1], "igemm: prec %d needs the lo activation plane in[1]", a.prec);
@@ -501,6 +344,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     B200DN_CHECK_ARG(a.H % 2 == 0 && a.W % 2 == 0, "igemm: DOWN2X2 needs even H, W (got %d x %d)", a.H, a.W);
   if (int rc = require_sm100()) return rc;
   if (int rc = get_encoder()) return rc;
+  const bool slab = a.mode == B200DN_MODE_CONV3X3 && (a.impl ? a.impl : default_conv3x3_impl()) == 2;
 
   KParams p;
   memset(&p, 0, sizeof(p));
@@ -532,18 +376,22 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   p.num_n_tiles = p.n_tiles_per_group * n_groups;
   int sms = device_sm_count();
   if (sms <= 0) return B200DN_E_CUDA;
-  // two x-adjacent A tiles per stage (M = 256 per W tile) when N is small enough for 4 accumulators in TMEM
-  // and there is enough work to keep every SM busy with the halved tile count
+  // accumulator tile: 16 x 8 pixels (tap kernel, sub-tiles side by side) or 8 x 16 (slab kernel, sub-tiles stacked)
+  const int tw1 = slab ? SLAB_TILE_W : TILE_W, th1 = slab ? SLAB_TILE_H : TILE_H;
+  // two A tiles per W tile (M = 256) when N is small enough for 4 accumulators in TMEM and there is enough
+  // work to keep every SM busy with the halved tile count
   int mt = a.m_tiles;
   B200DN_CHECK_ARG(mt >= 0 && mt <= 2, "igemm: m_tiles %d invalid", mt);
   if (mt == 2) B200DN_CHECK_ARG(block_n <= 128, "igemm: m_tiles=2 needs block_n <= 128 (TMEM columns)");
   if (mt == 0) {
-    const int64_t tiles2 = static_cast<int64_t>(p.B) * cdiv(p.W, 2 * TILE_W) * cdiv(p.H, TILE_H) * p.num_n_tiles;
+    const int64_t tiles2 = slab ? static_cast<int64_t>(p.B) * cdiv(p.W, tw1) * cdiv(p.H, 2 * th1) * p.num_n_tiles
+                                : static_cast<int64_t>(p.B) * cdiv(p.W, 2 * tw1) * cdiv(p.H, th1) * p.num_n_tiles;
     mt = (block_n <= 128 && tiles2 >= 2 * sms) ? 2 : 1;
   }
   p.mt = mt;
-  p.tiles_x = cdiv(p.W, TILE_W * mt);
-  p.tiles_y = cdiv(p.H, TILE_H);
+  const int stw = slab ? tw1 : tw1 * mt, sth = slab ? th1 * mt : th1;   // super-tile extent
+  p.tiles_x = cdiv(p.W, stw);
+  p.tiles_y = cdiv(p.H, sth);
   p.num_tiles = p.B * p.tiles_x * p.tiles_y * p.num_n_tiles;
   p.fmt = (a.prec == B200DN_PREC_FP16 || a.prec == B200DN_PREC_FP16X2) ? 0 : 1;
   switch (a.prec) {
@@ -563,9 +411,19 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
       p.n_pairs = 1;
       p.pair_w[0] = 0, p.pair_a[0] = 0;
   }
-  p.stage_bytes = mt * A_BYTES + block_n * 128;
-  p.num_stages = RING_BYTES / p.stage_bytes;
-  if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
+  if (slab) {
+    p.slab_w = 16;                                              // slab row pitch in pixels: SBO = 16 * 128 B
+    p.slab_bytes = p.slab_w * (SLAB_TILE_H * mt + 2) * 128;     // 36 KB (mt 1) / 68 KB (mt 2), multiples of 1 KB
+    p.num_slabs = (mt == 1 && block_n <= 128) ? 3 : 2;         // N = 256: trade a slab for a 4th W stage
+    p.stage_bytes = block_n * 128;                              // W ring stage
+    p.num_stages = (SLAB_DATA_BYTES - p.num_slabs * p.slab_bytes) / p.stage_bytes;
+    if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
+    p.bo_mode = slab_bo_mode();
+  } else {
+    p.stage_bytes = mt * A_BYTES + block_n * 128;
+    p.num_stages = RING_BYTES / p.stage_bytes;
+    if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
+  }
   int cols = 32;
   while (cols < 2 * mt * block_n) cols <<= 1;
   p.tmem_cols = cols;
@@ -623,7 +481,11 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
       uint64_t str[3] = {ct * 2, static_cast<uint64_t>(a.W) * ct * 2,
                          static_cast<uint64_t>(a.H) * static_cast<uint64_t>(a.W) * ct * 2};
       uint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
-      if (int rc = encode(tm, dt, 4, a.in[pl], dims, str, box, "A")) return rc;
+      if (slab) {
+        box[1] = static_cast<uint32_t>(p.slab_w);
+        box[2] = static_cast<uint32_t>(SLAB_TILE_H * mt + 2);
+      }
+      if (int rc = encode(tm, dt, 4, a.in[pl], dims, str, box, slab ? "A/slab" : "A")) return rc;
     }
   }
   {
@@ -635,6 +497,10 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
   }
 
+  int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
+  if (slab) return launch_conv3x3_slab(p, grid, stream);
+
   using KernelFn = void (*)(KParams);
   static const KernelFn kernels[3][2] = {{igemm_kernel<0, 1>, igemm_kernel<0, 2>},
                                          {igemm_kernel<1, 1>, igemm_kernel<1, 2>},
@@ -645,9 +511,6 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
         g_attr_err = cudaFuncSetAttribute(kernels[m][t], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(igemm_kernel, smem)");
-
-  int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
   const int mode_idx = a.mode == B200DN_MODE_CONV3X3 ? 0 : a.mode == B200DN_MODE_DOWN2X2 ? 1 : 2;
   kernels[mode_idx][mt - 1]<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
   B200DN_CUDA(cudaGetLastError());

@@ -62,7 +62,8 @@ def _(weight, prec, transposed):
     return weight.new_empty(L.b200dn_packed_weight_bytes(cout, cin, groups, prec) // 2, dtype=torch.int16)
 
 
-def _fill_common(a: IgemmArgs, mode, prec, x_hi, x_lo, cin, cout, wpacked, bias, slope, block_n, max_ctas, m_tiles=0):
+def _fill_common(a: IgemmArgs, mode, prec, x_hi, x_lo, cin, cout, wpacked, bias, slope, block_n, max_ctas, m_tiles=0,
+                 impl=0):
     B, H, W, ctot = x_hi.shape
     a.mode, a.prec = mode, prec
     a.B, a.H, a.W = B, H, W
@@ -70,7 +71,7 @@ def _fill_common(a: IgemmArgs, mode, prec, x_hi, x_lo, cin, cout, wpacked, bias,
     a.in_[0], a.in_[1] = _ptr(x_hi), _ptr(x_lo)
     a.in_ctot = ctot
     a.wpacked, a.bias, a.slope = _ptr(wpacked), _ptr(bias), _ptr(slope)
-    a.block_n, a.max_ctas, a.m_tiles = block_n, max_ctas, m_tiles
+    a.block_n, a.max_ctas, a.m_tiles, a.impl = block_n, max_ctas, m_tiles, impl
 
 
 @torch.library.custom_op("b200dn::conv_igemm", mutates_args=("out_hi", "out_lo"))
@@ -78,12 +79,12 @@ def conv_igemm(x_hi: torch.Tensor, x_lo: Optional[torch.Tensor], wpacked: torch.
                slope: Optional[torch.Tensor], mode: int, prec: int, cin: int, cout: int,
                out_hi: torch.Tensor, out_lo: Optional[torch.Tensor], out_coff: int,
                res_hi: Optional[torch.Tensor], res_lo: Optional[torch.Tensor],
-               block_n: int = 0, max_ctas: int = 0, m_tiles: int = 0) -> None:
+               block_n: int = 0, max_ctas: int = 0, m_tiles: int = 0, impl: int = 0) -> None:
     """conv (3x3 / 2x2-s2 / transposed 2x2-s2) + bias + PReLU (+ NHWC residual) into a channel slice of
     ``out_*`` ([B, Ho, Wo, ctot] int16 storage of bf16/fp16)."""
     _cuda(x_hi, x_lo, wpacked, bias, slope, out_hi, out_lo, res_hi, res_lo)
     a = IgemmArgs()
-    _fill_common(a, mode, prec, x_hi, x_lo, cin, cout, wpacked, bias, slope, block_n, max_ctas, m_tiles)
+    _fill_common(a, mode, prec, x_hi, x_lo, cin, cout, wpacked, bias, slope, block_n, max_ctas, m_tiles, impl)
     a.out_kind = _lib.OUT_NHWC16
     a.out[0], a.out[1] = _ptr(out_hi), _ptr(out_lo)
     a.out_ctot, a.out_coff = out_hi.shape[-1], out_coff
@@ -98,11 +99,11 @@ def conv_igemm(x_hi: torch.Tensor, x_lo: Optional[torch.Tensor], wpacked: torch.
 @torch.library.custom_op("b200dn::conv_out_nchw", mutates_args=("out",))
 def conv_out_nchw(x_hi: torch.Tensor, x_lo: Optional[torch.Tensor], wpacked: torch.Tensor, bias: torch.Tensor,
                   slope: Optional[torch.Tensor], prec: int, cin: int, cout: int,
-                  residual: Optional[torch.Tensor], out: torch.Tensor, res_bmod: int = 0) -> None:
+                  residual: Optional[torch.Tensor], out: torch.Tensor, res_bmod: int = 0, impl: int = 0) -> None:
     """OutputBlock.conv_2 + PReLU + `+ inputs` with fp32 NCHW output (UNet/RDUNet_model.py:83-93,186)."""
     _cuda(x_hi, x_lo, wpacked, bias, slope, residual, out)
     a = IgemmArgs()
-    _fill_common(a, _lib.MODE_CONV3X3, prec, x_hi, x_lo, cin, cout, wpacked, bias, slope, 0, 0)
+    _fill_common(a, _lib.MODE_CONV3X3, prec, x_hi, x_lo, cin, cout, wpacked, bias, slope, 0, 0, 0, impl)
     a.out_kind = _lib.OUT_NCHW32
     a.out_nchw, a.res_nchw, a.res_bmod = _ptr(out), _ptr(residual), res_bmod
     with torch.cuda.device(x_hi.device):
