@@ -167,6 +167,49 @@ def test_rdunet128_full_size_patch_vs_oracle(built_lib):
                 assert mx <= bound, f"{precision}: max err {mx:.3e}"
 
 
+def test_tiled_image_equals_untiled(built_lib):
+    """BASELINE config 5 in small: halo-200 tiling (receptive-field radius 193) reproduces the untiled forward
+    bit for bit; the only zero padding is at true image borders."""
+    torch.manual_seed(1)
+    net = b2.RDUNet(base_filters=16).to(DEV).eval()
+    img = torch.rand(1, 3, 512, 768, device=DEV) * 2 - 1
+    with torch.no_grad():
+        full = net(img)
+        tiled = b2.sharding.denoise_tiled(net, img, rows=2, cols=2)
+        assert torch.equal(full, tiled)
+        small_halo = b2.sharding.denoise_tiled(net, img, rows=2, cols=2, halo=64)
+        assert not torch.equal(full, small_halo)
+
+
+def test_sidd_shaped_pipeline_vs_oracle(built_lib):
+    """BASELINE config 4 in small: u8 blocks -> normalise -> sampler -> quantise + PSNR/SSIM (R = 2), against the
+    oracle's arithmetic for every stage (benchmark.py:32-46, evaluate_SIDD.py:63-64)."""
+    from oracle import metrics_oracle as mo, noise_oracle as no
+    torch.manual_seed(5)
+    dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=16), timesteps=3).eval()
+    sd = {k: v.clone() for k, v in dm.state_dict().items()}
+    dm = dm.to(DEV)
+    rng = np.random.default_rng(3)
+    gt_u8 = rng.integers(0, 256, size=(2, 32, 32, 3), dtype=np.uint8)
+    noisy_u8, _, clean = b2.noise.add_gaussian_noise(torch.from_numpy(gt_u8).to(DEV), 25.0, seed=9)
+    noisy = b2.noise.u8_to_normalized(noisy_u8)
+    den = dm.improved_sampling(noisy)
+    out_u8 = b2.noise.normalized_to_u8(den)
+    psnr, ssim = b2.metrics.batch_metrics(clean, den, 2.0)
+    # oracle chain on the CPU
+    r_noisy_u8, r_noisy, r_clean = no.degrade(gt_u8, 25.0, seed=9)
+    assert np.array_equal(noisy_u8.cpu().numpy(), r_noisy_u8) and np.array_equal(noisy.cpu().numpy(), r_noisy)
+    with torch.no_grad():
+        r_den = orc.improved_sampling(sd, torch.from_numpy(r_noisy), 3)
+    _check_bar(den.cpu(), r_den, what="SIDD-shaped sampler")
+    # quantiser is exact on the same input
+    assert np.array_equal(out_u8.cpu().numpy(), no.norm_to_u8(den.cpu().numpy()))
+    for i in range(2):
+        g, o = r_clean[i].transpose(1, 2, 0), den[i].cpu().numpy().transpose(1, 2, 0)
+        assert float(psnr[i]) == pytest.approx(mo.peak_signal_noise_ratio(g, o, data_range=2), abs=1e-4)
+        assert float(ssim[i]) == pytest.approx(mo.structural_similarity(g, o, data_range=2, channel_axis=-1), abs=1e-5)
+
+
 def test_module_contract(built_lib):
     net = b2.RDUNet(base_filters=16).to(DEV).eval()
     with torch.no_grad():

@@ -9,82 +9,95 @@ namespace b200dn {
 
 namespace {
 
-constexpr int PX = 32;  // pixels along W per block
+constexpr int PX = 32;     // pixels along W per block (one warp = 32 consecutive pixels: coalesced NCHW reads)
+constexpr int ROWS = 8;    // rows per pass (one warp each)
+constexpr int PASSES = 4;  // a block covers PX x (ROWS * PASSES) pixels, so the weights are staged once per 1024 px
 
+// One thread = one pixel, all output channels in groups of 8 (weights broadcast from shared memory).
 template <int CIN>
-__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int Bx, const float* __restrict__ t,
-                                                      int64_t t_sb, int64_t t_sh, int64_t t_sw, int H, int W, int cout,
-                                                      const float* __restrict__ w, const float* __restrict__ bias,
-                                                      const float* __restrict__ slope, int prec,
-                                                      uint16_t* __restrict__ out0, uint16_t* __restrict__ out1,
-                                                      int out_ctot) {
-  extern __shared__ float w_s[];  // [CIN*9][cout]
+__global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restrict__ x, int Bx,
+                                                            const float* __restrict__ t, int64_t t_sb, int64_t t_sh,
+                                                            int64_t t_sw, int H, int W, int cout,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            const float* __restrict__ slope, int prec,
+                                                            uint16_t* __restrict__ out0, uint16_t* __restrict__ out1,
+                                                            int out_ctot) {
+  extern __shared__ float w_s[];  // [CIN*9][cout], then bias[cout], slope[cout]
   constexpr int K = CIN * 9;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const int nthr = blockDim.x * blockDim.y;
-  for (int i = tid; i < K * cout; i += nthr) {
+  float* b_s = w_s + K * cout;
+  float* s_s = b_s + cout;
+  const int tid = threadIdx.y * PX + threadIdx.x;
+  for (int i = tid; i < K * cout; i += PX * ROWS) {
     const int o = i / K, k = i - o * K;  // w is [o][ci][ky][kx] = [o][k]
     w_s[k * cout + o] = w[i];
+  }
+  for (int i = tid; i < cout; i += PX * ROWS) {
+    b_s[i] = bias[i];
+    s_s[i] = slope[i];
   }
   __syncthreads();
 
   const int b = blockIdx.z;
-  const int y = blockIdx.y;
   const int xx = blockIdx.x * PX + threadIdx.x;
-  if (xx >= W) return;
   const int64_t hw = static_cast<int64_t>(H) * W;
   const float* xb = x + static_cast<int64_t>(b % Bx) * 3 * hw;
-
-  float v[K];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int yy = y + ky - 1, xc = xx + kx - 1;
-      const bool in = (yy >= 0) && (yy < H) && (xc >= 0) && (xc < W);
-      const int64_t sp = static_cast<int64_t>(yy) * W + xc;
-#pragma unroll
-      for (int ci = 0; ci < 3; ++ci) v[ci * 9 + ky * 3 + kx] = in ? __ldg(xb + ci * hw + sp) : 0.f;
-      if (CIN == 4) v[27 + ky * 3 + kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
-    }
-  }
-
-  const int64_t pix = (static_cast<int64_t>(b) * H + y) * W + xx;
   const bool is_bf16 = (prec != B200DN_PREC_FP16) && (prec != B200DN_PREC_FP16X2);
-  for (int g = threadIdx.y; g * 8 < cout; g += blockDim.y) {
-    float acc[8];
+  if (xx >= W) return;
+
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const int y = (blockIdx.y * PASSES + pass) * ROWS + threadIdx.y;
+    if (y >= H) break;
+    float v[K];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8 + 4);
-      acc[0] = fmaf(v[k], w0.x, acc[0]);
-      acc[1] = fmaf(v[k], w0.y, acc[1]);
-      acc[2] = fmaf(v[k], w0.z, acc[2]);
-      acc[3] = fmaf(v[k], w0.w, acc[3]);
-      acc[4] = fmaf(v[k], w1.x, acc[4]);
-      acc[5] = fmaf(v[k], w1.y, acc[5]);
-      acc[6] = fmaf(v[k], w1.z, acc[6]);
-      acc[7] = fmaf(v[k], w1.w, acc[7]);
-    }
-    uint32_t hi[4], lo[4];
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = y + ky - 1, xc = xx + kx - 1;
+        const bool in = (yy >= 0) && (yy < H) && (xc >= 0) && (xc < W);
+        const int64_t sp = static_cast<int64_t>(yy) * W + xc;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = acc[2 * j] + __ldg(bias + g * 8 + 2 * j);
-      float c = acc[2 * j + 1] + __ldg(bias + g * 8 + 2 * j + 1);
-      a = a > 0.f ? a : a * __ldg(slope + g * 8 + 2 * j);
-      c = c > 0.f ? c : c * __ldg(slope + g * 8 + 2 * j + 1);
-      if (is_bf16) {
-        hi[j] = pack_bf16x2(a, c);
-        lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), c - bf16_hi(hi[j]));
-      } else {
-        hi[j] = pack_f16x2(a, c);
-        lo[j] = pack_f16x2(a - f16_lo(hi[j]), c - f16_hi(hi[j]));
+        for (int ci = 0; ci < 3; ++ci) v[ci * 9 + ky * 3 + kx] = in ? __ldg(xb + ci * hw + sp) : 0.f;
+        if (CIN == 4) v[27 + ky * 3 + kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
       }
     }
-    *reinterpret_cast<uint4*>(out0 + pix * out_ctot + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    if (out1 != nullptr) *reinterpret_cast<uint4*>(out1 + pix * out_ctot + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    const int64_t pix = (static_cast<int64_t>(b) * H + y) * W + xx;
+    uint16_t* o0 = out0 + pix * out_ctot;
+    uint16_t* o1 = out1 ? out1 + pix * out_ctot : nullptr;
+    for (int g = 0; g * 8 < cout; ++g) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8 + 4);
+        acc[0] = fmaf(v[k], w0.x, acc[0]);
+        acc[1] = fmaf(v[k], w0.y, acc[1]);
+        acc[2] = fmaf(v[k], w0.z, acc[2]);
+        acc[3] = fmaf(v[k], w0.w, acc[3]);
+        acc[4] = fmaf(v[k], w1.x, acc[4]);
+        acc[5] = fmaf(v[k], w1.y, acc[5]);
+        acc[6] = fmaf(v[k], w1.z, acc[6]);
+        acc[7] = fmaf(v[k], w1.w, acc[7]);
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = acc[2 * j] + b_s[g * 8 + 2 * j];
+        float c = acc[2 * j + 1] + b_s[g * 8 + 2 * j + 1];
+        a = a > 0.f ? a : a * s_s[g * 8 + 2 * j];
+        c = c > 0.f ? c : c * s_s[g * 8 + 2 * j + 1];
+        if (is_bf16) {
+          hi[j] = pack_bf16x2(a, c);
+          lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), c - bf16_hi(hi[j]));
+        } else {
+          hi[j] = pack_f16x2(a, c);
+          lo[j] = pack_f16x2(a - f16_lo(hi[j]), c - f16_hi(hi[j]));
+        }
+      }
+      *reinterpret_cast<uint4*>(o0 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      if (o1 != nullptr) *reinterpret_cast<uint4*>(o1 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
   }
 }
 
@@ -102,14 +115,12 @@ extern "C" int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_
   B200DN_CHECK_ARG(prec >= 0 && prec <= 4, "conv_in: bad prec %d", prec);
   const bool two = (prec == B200DN_PREC_BF16X2 || prec == B200DN_PREC_BF16X3 || prec == B200DN_PREC_FP16X2);
   B200DN_CHECK_ARG(!two || out1, "conv_in: prec %d needs the lo output plane", prec);
-  B200DN_CHECK_ARG(B <= 65535 && H <= 65535, "conv_in: B/H exceed the grid limit");
+  B200DN_CHECK_ARG(B <= 65535 && H <= 65535 * ROWS * PASSES, "conv_in: B/H exceed the grid limit");
   if (int rc = require_sm100()) return rc;
   const int cin = t ? 4 : 3;
-  const size_t smem = static_cast<size_t>(cin) * 9 * cout * sizeof(float);
+  const size_t smem = (static_cast<size_t>(cin) * 9 + 2) * cout * sizeof(float);
   B200DN_CHECK_ARG(smem <= 160 * 1024, "conv_in: cout %d too large", cout);
-  int ny = cout / 8;
-  if (ny > 8) ny = 8;
-  dim3 block(PX, ny), grid(cdiv(W, PX), H, B);
+  dim3 block(PX, ROWS), grid(cdiv(W, PX), cdiv(H, ROWS * PASSES), B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint16_t* o0 = static_cast<uint16_t*>(out0);
   uint16_t* o1 = two ? static_cast<uint16_t*>(out1) : nullptr;
