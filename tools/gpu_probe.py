@@ -50,9 +50,12 @@ def conv_case(B, H, W, cin, cout, prec, mode=_lib.MODE_CONV3X3, block_n=0, impl=
     return rel
 
 
-def bench_layer(B, H, W, cin, cout, prec=_lib.PREC_BF16, mode=_lib.MODE_CONV3X3, block_n=0, iters=10, res=False, mt=0, impl=0):
+def bench_layer(B, H, W, cin, cout, prec=_lib.PREC_BF16, mode=_lib.MODE_CONV3X3, block_n=0, iters=10, res=False, mt=0, impl=0,
+                ctot=0, out_ctot=0):
     d = dt16(prec)
-    x_hi = (torch.randn(B, H, W, cin, device=DEV) * 0.5).to(d).view(torch.int16)
+    ctot = ctot or cin
+    out_ctot = out_ctot or cout
+    x_hi = (torch.randn(B, H, W, ctot, device=DEV) * 0.5).to(d).view(torch.int16)
     x_lo = torch.zeros_like(x_hi) if two_planes(prec) else None
     k = 3 if mode == _lib.MODE_CONV3X3 else 2
     w = torch.randn(cout, cin, k, k, device=DEV) * 0.02
@@ -60,20 +63,20 @@ def bench_layer(B, H, W, cin, cout, prec=_lib.PREC_BF16, mode=_lib.MODE_CONV3X3,
     bias = torch.zeros(cout, device=DEV)
     slope = torch.full((cout,), 0.25, device=DEV)
     Ho, Wo = (H, W) if mode == _lib.MODE_CONV3X3 else (H // 2, W // 2)
-    out_hi = torch.empty((B, Ho, Wo, cout), dtype=torch.int16, device=DEV)
+    out_hi = torch.empty((B, Ho, Wo, out_ctot), dtype=torch.int16, device=DEV)
     out_lo = torch.empty_like(out_hi) if two_planes(prec) else None
     r_hi = x_hi if res else None
     a = _lib.IgemmArgs()
     a.mode, a.prec, a.B, a.H, a.W, a.cin, a.cout = mode, prec, B, H, W, cin, cout
     a.in_[0], a.in_[1] = x_hi.data_ptr(), (x_lo.data_ptr() if x_lo is not None else None)
-    a.in_ctot = cin
+    a.in_ctot = ctot
     a.wpacked, a.bias, a.slope = wp.data_ptr(), bias.data_ptr(), slope.data_ptr()
     a.out_kind = 0
     a.out[0], a.out[1] = out_hi.data_ptr(), (out_lo.data_ptr() if out_lo is not None else None)
-    a.out_ctot, a.out_coff = cout, 0
+    a.out_ctot, a.out_coff = out_ctot, 0
     if res:
         a.res[0] = r_hi.data_ptr()
-        a.res_ctot = cin
+        a.res_ctot = ctot
     a.block_n = block_n
     a.m_tiles = mt
     a.impl = impl
