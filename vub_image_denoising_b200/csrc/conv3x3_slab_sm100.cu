@@ -39,7 +39,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint3
   return make_sw128_desc(smem_addr, sbo_bytes) | (static_cast<uint64_t>(base_off & 7u) << 49);
 }
 
-template <int MT>
+// WRES: the layer's whole packed weight set ([w plane][64-ch block][tap][N x 64]) is loaded into shared memory once
+// per CTA and stays resident; the main loop then only streams slabs.  Used for the small layers (F = 32 levels 0/1),
+// which are latency-bound: per tile it removes 9 W-tile round trips and keeps the issue loop small enough for the
+// instruction cache (ncu: the unrolled 9-tap path showed mostly `no_inst` stalls there).
+template <int MT, bool WRES>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -117,6 +121,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
       }
     }
   } else if (warp == 2) {
+    if (WRES) {
+      // ===================================================== resident weights: 9 taps per box, loaded once
+      if (elect_one()) {
+        const int n_boxes = p.n_wplanes * n_cblk;
+        const uint32_t box_bytes = static_cast<uint32_t>(9 * block_n * 128);
+        const uint32_t full = bars + B_W_FULL;
+        mbar_arrive_expect_tx(full, static_cast<uint32_t>(n_boxes) * box_bytes);
+        for (int wp = 0; wp < p.n_wplanes; ++wp)
+          for (int cb = 0; cb < n_cblk; ++cb)
+            tma_load_3d(wring + static_cast<uint32_t>(wp * n_cblk + cb) * box_bytes, &p.tmW, full, cb * BLOCK_K, 0,
+                        wp * 9);
+      }
+      __syncwarp();
+    } else {
     // ===================================================== W-tile TMA producer: one [N x 64] tile per tap
     int ws = 0;
     uint32_t wph = 0;
@@ -144,6 +162,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
         }
       }
     }
+    }
   } else if (warp == 1 || (warp == 3 && MT == 2)) {
     // ===================================================== MMA issuer of sub-tile j
     const int j = warp == 1 ? 0 : 1;
@@ -152,6 +171,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
     const int last_k16 = p.last_k16;
     const uint32_t pitch = static_cast<uint32_t>(p.slab_w * 128);   // bytes per slab pixel row = SBO
     const uint32_t bo_mode = static_cast<uint32_t>(p.bo_mode);
+    const int pw_0 = p.pair_w[0], pw_1 = p.pair_w[1], pw_2 = p.pair_w[2];
+    const uint32_t w_tile_bytes = static_cast<uint32_t>(block_n * 128);
+    if (WRES) mbar_wait(bars + B_W_FULL, 0);   // resident weights have landed
     int s = 0, ws = 0;
     uint32_t sph = 0, wph = 0;
     int local_tile = 0;
@@ -167,6 +189,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
         const bool full_block = (cb != n_cblk - 1) || (last_k16 == BLOCK_K / 16);
         mbar_wait(bars + B_SLAB_FULL + s * 8, sph);
         const uint32_t slab = smem_base + static_cast<uint32_t>(s * slab_bytes) + static_cast<uint32_t>(j * TH) * pitch;
+        if (WRES) {
+          // resident weights: [w plane][cb][tap][N x 64]; pair index = kc / n_cblk
+          const int pair = kc / n_cblk;
+          const int wpl = pair == 0 ? pw_0 : pair == 1 ? pw_1 : pw_2;
+          const uint32_t w_cb = wring + static_cast<uint32_t>((wpl * n_cblk + cb) * 9) * w_tile_bytes;
+          tc_fence_after();
+          if (elect_one()) {
+            const int nk = full_block ? BLOCK_K / 16 : last_k16;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              const uint32_t a_addr = slab + static_cast<uint32_t>(dy) * pitch + static_cast<uint32_t>(dx * 128);
+              const uint64_t adesc = make_sw128_desc(a_addr, pitch);
+              const uint64_t bdesc = make_sw128_desc(w_cb + static_cast<uint32_t>(tap) * w_tile_bytes, 1024);
+#pragma unroll 1
+              for (int k = 0; k < nk; ++k) {
+                umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+            umma_commit(bars + B_SLAB_EMPTY + s * 8);
+            if (kc == kc_iters - 1) umma_commit(bars + B_TFULL + acc * 8);
+          }
+          __syncwarp();
+          accumulate = 1;
+        } else {
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3, dx = tap % 3;
@@ -200,6 +248,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
           }
           __syncwarp();
           accumulate = 1;
+        }
         }
         if (++s == num_slabs) {
           s = 0;
@@ -257,18 +306,18 @@ cudaError_t g_err = cudaSuccess;
 }  // namespace
 
 int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream) {
-  B200DN_CHECK_ARG(p.num_stages >= 2, "conv3x3 slab: W ring too small for block_n %d", p.block_n);
+  B200DN_CHECK_ARG(p.wres || p.num_stages >= 2, "conv3x3 slab: W ring too small for block_n %d", p.block_n);
   B200DN_CHECK_ARG(p.num_slabs <= MAX_SLABS, "conv3x3 slab: too many slabs");
+  using KernelFn = void (*)(KParams);
+  static const KernelFn kernels[2][2] = {{conv3x3_slab_kernel<1, false>, conv3x3_slab_kernel<1, true>},
+                                         {conv3x3_slab_kernel<2, false>, conv3x3_slab_kernel<2, true>}};
   std::call_once(g_once, [] {
-    g_err = cudaFuncSetAttribute(conv3x3_slab_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB);
-    if (g_err == cudaSuccess)
-      g_err = cudaFuncSetAttribute(conv3x3_slab_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB);
+    for (int m = 0; m < 2 && g_err == cudaSuccess; ++m)
+      for (int w = 0; w < 2 && g_err == cudaSuccess; ++w)
+        g_err = cudaFuncSetAttribute(kernels[m][w], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB);
   });
   if (g_err != cudaSuccess) return cuda_fail(g_err, "cudaFuncSetAttribute(conv3x3_slab_kernel, smem)");
-  if (p.mt == 2)
-    conv3x3_slab_kernel<2><<<grid, NUM_THREADS, SMEM_BYTES_SLAB, stream>>>(p);
-  else
-    conv3x3_slab_kernel<1><<<grid, NUM_THREADS, SMEM_BYTES_SLAB, stream>>>(p);
+  kernels[p.mt - 1][p.wres ? 1 : 0]<<<grid, NUM_THREADS, SMEM_BYTES_SLAB, stream>>>(p);
   B200DN_CUDA(cudaGetLastError());
   return 0;
 }

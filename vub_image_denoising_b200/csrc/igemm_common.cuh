@@ -31,6 +31,7 @@ struct __align__(64) KParams {
   int num_stages, stage_bytes, tmem_cols;
   // slab kernel only
   int slab_w, slab_bytes, num_slabs, bo_mode;
+  int wres, n_wplanes;   // weights resident in shared memory (small layers)
   const float* bias;
   const float* slope;
   int out_kind;

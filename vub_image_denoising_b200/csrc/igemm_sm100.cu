@@ -319,6 +319,13 @@ int default_conv3x3_impl() {
   }();
   return impl;
 }
+bool wres_enabled() {
+  static int on = [] {
+    const char* e = getenv("B200DN_SLAB_WRES");
+    return e ? atoi(e) : 1;
+  }();
+  return on != 0;
+}
 int slab_bo_mode() {
   static int mode = [] {
     const char* e = getenv("B200DN_SLAB_BO");
@@ -419,6 +426,10 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     p.num_stages = (SLAB_DATA_BYTES - p.num_slabs * p.slab_bytes) / p.stage_bytes;
     if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
     p.bo_mode = slab_bo_mode();
+    // small layers: keep the whole packed weight set resident in shared memory (single N tile only)
+    p.n_wplanes = two_w ? 2 : 1;
+    const int64_t w_all = static_cast<int64_t>(p.n_wplanes) * p.n_cblk * 9 * block_n * 128;
+    p.wres = (p.num_n_tiles == 1 && w_all <= SLAB_DATA_BYTES - p.num_slabs * p.slab_bytes && wres_enabled()) ? 1 : 0;
   } else {
     p.stage_bytes = mt * A_BYTES + block_n * 128;
     p.num_stages = RING_BYTES / p.stage_bytes;
@@ -493,7 +504,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(cout_pad),
                         static_cast<uint64_t>(p.wgroups) * (two_w ? 2 : 1)};
     uint64_t str[2] = {static_cast<uint64_t>(cin_pad) * 2, static_cast<uint64_t>(cin_pad) * cout_pad * 2};
-    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(block_n), 1};
+    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(block_n), p.wres ? 9u : 1u};   // resident mode: all 9 taps per box
     if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
   }
 
