@@ -247,9 +247,17 @@ def run_b200(args) -> None:
     flops_in_conv = 2 * 9 * 3 * F * PATCH * PATCH
     igemm_flops = (flops_img - flops_in_conv) * B
     achieved = igemm_flops / (igemm_last_ms / 1e3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "igemm_kernel (68 launches per step)", "achieved": achieved,
-                "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "traffic": None, "peak_source": peaks["source"],
+    # DRAM traffic of the same 68 launches from the committed ncu pass over this command (profiles/), per launch
+    traffic = None
+    summ = ROOT / "profiles" / "r01_bench_launches_summary.json"
+    if summ.exists() and F == 128 and B == 64:
+        traffic = json.loads(summ.read_text())["tensor_core_kernels"]["dram_bytes_per_launch"]
+    roofline = {"bound": "tensor", "kernel": "conv3x3_slab_kernel + igemm_kernel (68 tcgen05 launches per step)",
+                "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write per launch, mean over the 68 launches (ncu, profiles/r01_bench_launches.csv); "
+                                "algorithmic layer-by-layer bytes are 1.83 GB per launch, so L2 already absorbs re-reads",
+                "peak_source": peaks["source"],
                 "algorithmic_flops_per_step": igemm_flops, "kernel_ms_per_step": igemm_last_ms,
                 "kernel_share_of_step": igemm_last_ms / ms_step}
 
