@@ -255,3 +255,37 @@ def test_linearity_of_sampler_step_and_idempotent_shapes(built_lib):
     for t in range(20, 0, -1):
         x = orc.sampler_step(x, x, x, y.cpu(), t, 20)
     assert torch.equal(out.cpu(), x)
+
+
+@pytest.mark.parametrize("base_filters,shape", [(16, (1, 3, 8, 8)), (16, (3, 3, 8, 24)), (48, (1, 3, 40, 56)), (32, (5, 3, 24, 16)),
+                                                  (16, (2, 3, 136, 72))])
+def test_ragged_shapes_and_widths_vs_oracle(base_filters, shape, built_lib):
+    """Edge cases: the smallest legal image (8x8 -> 1x1 at the deepest level), non-power-of-two widths
+    (base_filters = 48 -> 24-channel growth, N padded to 32), odd batches, sizes that are not multiples of the
+    8x16 / 16x8 accumulator tiles."""
+    torch.manual_seed(base_filters + shape[2])
+    net = b2.RDUNet(base_filters=base_filters).eval()
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(*shape, generator=g) * 2 - 1
+    with torch.no_grad():
+        ref = orc.rdunet_forward(net.state_dict(), x)
+        net = net.to(DEV)
+        net.precision = "bf16x3"
+        got = net(x.to(DEV)).cpu()
+        assert float((got - ref).abs().max()) <= 1e-4
+        net.precision = "fp16"
+        got = net(x.to(DEV)).cpu()
+        _check_bar(got, ref, what=f"RDUNet({base_filters}) {shape} fp16")
+
+
+def test_unsupported_configurations_raise(built_lib):
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="multiple of 16"):
+            b2.RDUNet(base_filters=24).to(DEV).eval()(torch.zeros(1, 3, 16, 16, device=DEV))
+        gray = b2.RDUNet(channels=1, base_filters=16).to(DEV).eval()
+        with pytest.raises(RuntimeError, match="3-channel"):
+            gray(torch.zeros(1, 1, 16, 16, device=DEV))
+        net = b2.RDUNet(base_filters=16).to(DEV).eval()
+        net.precision = "int8"
+        with pytest.raises(RuntimeError, match="unknown precision"):
+            net(torch.zeros(1, 3, 16, 16, device=DEV))

@@ -136,32 +136,29 @@ class _RDUNetBase(nn.Module):
         self.apply(init_weights())
         # private caches (not parameters / buffers -> invisible to state_dict)
         self._plans: dict = {}
-        self._packs: dict = {}
         self.precision = DEFAULT_PREC
 
     # ---- nn.Module plumbing that must drop caches
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
-        self._plans, self._packs = {}, {}
+        self._plans = {}
         return out
 
     def __deepcopy__(self, memo):
         import copy
-        plans, packs = self._plans, self._packs
-        self._plans, self._packs = {}, {}
+        plans, self._plans = self._plans, {}      # plans hold raw device pointers: never copy them
         try:
-            cls = self.__class__
-            new = cls.__new__(cls)
+            new = self.__class__.__new__(self.__class__)
             memo[id(self)] = new
             for key, val in self.__dict__.items():
                 new.__dict__[key] = copy.deepcopy(val, memo)
         finally:
-            self._plans, self._packs = plans, packs
+            self._plans = plans
         return new
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        state["_plans"], state["_packs"] = {}, {}
+        state["_plans"] = {}
         return state
 
     # ---- helpers
@@ -272,6 +269,9 @@ class ForwardPlan:
         F = net.base_filters
         if F % 16:
             raise RuntimeError(f"base_filters={F}: the B200 kernels need a multiple of 16")
+        if net._img_channels != 3 or net._out_channels != 3:
+            raise RuntimeError("the B200 path implements the reference's 3-channel (RGB) networks; "
+                               f"got channels={net._img_channels} in / {net._out_channels} out")
         self.lib = _lib.lib()
         self.prec = _lib.PREC_NAMES[precision]
         self.precision = precision
