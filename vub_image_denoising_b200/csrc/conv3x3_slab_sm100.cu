@@ -29,7 +29,8 @@ namespace {
 constexpr int TW = SLAB_TILE_W;   // 8
 constexpr int TH = SLAB_TILE_H;   // 16
 constexpr int MAX_SLABS = 3;
-constexpr int SMEM_BYTES_SLAB = 1024 + SLAB_DATA_BYTES + 256 + 2 * 2 * MAX_N * 4;
+constexpr int DATA_BYTES = SLAB_DATA_BYTES + EPI_STAGING_BYTES;   // [slabs | W ring or resident W | epilogue staging]
+constexpr int SMEM_BYTES_SLAB = 1024 + DATA_BYTES + 256 + 2 * 2 * MAX_N * 4;
 
 // barrier map (byte offsets from `bars`)
 constexpr uint32_t B_SLAB_FULL = 0, B_SLAB_EMPTY = 24, B_W_FULL = 48, B_W_EMPTY = 112, B_TFULL = 176, B_TEMPTY = 192,
@@ -49,9 +50,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
-  const uint32_t bars = smem_base + SLAB_DATA_BYTES;
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + SLAB_DATA_BYTES + B_TMEM_PTR);
-  float* epi_bias = reinterpret_cast<float*>(smem_gen + SLAB_DATA_BYTES + 256);  // [2][MAX_N]
+  const uint32_t bars = smem_base + DATA_BYTES;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + DATA_BYTES + B_TMEM_PTR);
+  float* epi_bias = reinterpret_cast<float*>(smem_gen + DATA_BYTES + 256);  // [2][MAX_N]
   float* epi_slope = epi_bias + 2 * MAX_N;
 
   // Role index: hardware warps 4..7 run the single-thread producer / MMA-issue loops, warps 0..3 the epilogue.
@@ -270,6 +271,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
     const int H = p.H, W = p.W, cout = p.cout;
     const float* bias = p.bias;
     const float* slope = p.slope;
+    const bool staged = !WRES && p.epi_staged;
+    uint8_t* stg = smem_gen + SLAB_DATA_BYTES + we * 4096;
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
       const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
@@ -289,8 +292,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
         const int64_t pix = (static_cast<int64_t>(t.b) * H + y) * W + x;
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n);
-        epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, pix, pix, t.n0,
-                         j == MT - 1 ? bars + B_TEMPTY + acc * 8 : 0u);
+        const uint32_t rel = j == MT - 1 ? bars + B_TEMPTY + acc * 8 : 0u;
+        if (staged) {
+          RowMap rm;
+          rm.b = t.b, rm.y0 = t.y0 + j * TH, rm.x0 = t.x0, rm.tw_shift = 3, rm.H = H, rm.W = W, rm.up = 0, rm.ky = 0, rm.kx = 0;
+          epilogue_subtile_staged(ea, taddr, block_n, bs, ss, rm, we * 32, lane, t.n0, rel, stg);
+        } else {
+          epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, pix, pix, t.n0, rel);
+        }
       }
     }
   }

@@ -32,6 +32,7 @@ struct __align__(64) KParams {
   // slab kernel only
   int slab_w, slab_bytes, num_slabs, bo_mode;
   int wres, n_wplanes;   // weights resident in shared memory (small layers)
+  int epi_staged;        // smem-transposed epilogue with 128-byte-row global stores
   const float* bias;
   const float* slope;
   int out_kind;
@@ -208,6 +209,114 @@ __device__ __forceinline__ void epilogue_subtile(const EpiArgs& e, uint32_t tadd
   }
 }
 
+// ---- staged epilogue -------------------------------------------------------------------------------------
+// The direct epilogue above has every thread store 16 B of its own pixel: 32 different 128-byte lines per
+// warp instruction (32 L1 wavefronts for 512 useful bytes).  The staged variant transposes a [32 pixel x 64
+// channel] block through a per-warp 4 KB shared-memory buffer (16-byte chunks XOR-swizzled by the row, so both
+// the row-wise writes and the 4-rows-per-instruction reads are bank-conflict free) and then stores / loads whole
+// 128-byte pixel rows: 8 lanes per pixel, 4 pixels per warp instruction.  Single-plane formats, cout % 64 == 0.
+struct RowMap {
+  int b, y0, x0;       // image, tile origin (for the sub-tile)
+  int tw_shift;        // log2 of the accumulator tile width in pixels (4: tap kernel, 3: slab kernel)
+  int H, W;            // GEMM-M domain
+  int up, ky, kx;      // transposed conv: output pixel = (2y+ky, 2x+kx) in a 2H x 2W image
+};
+
+__device__ __forceinline__ bool row_pixels(const RowMap& m, int row, int64_t& out_pix, int64_t& res_pix) {
+  const int th = row >> m.tw_shift, tw = row & ((1 << m.tw_shift) - 1);
+  const int y = m.y0 + th, x = m.x0 + tw;
+  res_pix = (static_cast<int64_t>(m.b) * m.H + y) * m.W + x;
+  out_pix = m.up ? (static_cast<int64_t>(m.b) * (2 * m.H) + (2 * y + m.ky)) * (2 * m.W) + (2 * x + m.kx) : res_pix;
+  return (y < m.H) && (x < m.W);
+}
+
+__device__ __forceinline__ void epilogue_subtile_staged(const EpiArgs& e, uint32_t taddr, int block_n, const float* bs,
+                                                        const float* ss, const RowMap& m, int row0, int lane, int n0,
+                                                        uint32_t release_bar, uint8_t* stg) {
+  const uint32_t my_row = static_cast<uint32_t>(lane);
+  const int sub_row = lane >> 3, chunk = lane & 7;   // coalesced phases: 4 rows x 8 chunks per instruction
+  // per-lane addresses of its 8 coalesced rows (invariant over the channel groups of this sub-tile)
+  uint16_t* optr[8];
+  const uint16_t* rptr[8];
+  uint32_t okmask = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t op, rp;
+    const bool ok = row_pixels(m, row0 + i * 4 + sub_row, op, rp);
+    okmask |= (ok ? 1u : 0u) << i;
+    optr[i] = static_cast<uint16_t*>(e.out0) + op * e.out_ctot + e.out_coff + n0 + chunk * 8;
+    rptr[i] = static_cast<const uint16_t*>(e.res0) + rp * e.res_ctot + n0 + chunk * 8;
+  }
+  // staging offsets of those rows, and of this thread's own row (compute phase)
+  const uint32_t co_off = static_cast<uint32_t>(sub_row * 128 + ((chunk ^ sub_row) << 4));   // + i*512, XOR fixed below
+  (void)co_off;
+  for (int c0 = 0; c0 < block_n; c0 += 64) {
+    if (e.res0 != nullptr) {
+      // residual tile -> staging (coalesced 128-byte rows)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + sub_row;
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if ((okmask >> i) & 1u) q = __ldg(reinterpret_cast<const uint4*>(rptr[i] + c0));
+        *reinterpret_cast<uint4*>(stg + r * 128 + ((chunk ^ (r & 7)) << 4)) = q;
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      uint32_t r[16];
+      tmem_ld16(taddr + c0 + 16 * q4, r);
+      tmem_ld_wait();
+      if (release_bar != 0 && c0 + 64 >= block_n && q4 == 3) {
+        tc_fence_before();
+        mbar_arrive(release_bar);
+      }
+      float v[16];
+      const float4* b4 = reinterpret_cast<const float4*>(bs + c0 + 16 * q4);
+      const float4* s4 = reinterpret_cast<const float4*>(ss + c0 + 16 * q4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 bb = b4[q];
+        const float4 sl = s4[q];
+        float a;
+        a = __uint_as_float(r[4 * q + 0]) + bb.x;
+        v[4 * q + 0] = a > 0.f ? a : a * sl.x;
+        a = __uint_as_float(r[4 * q + 1]) + bb.y;
+        v[4 * q + 1] = a > 0.f ? a : a * sl.y;
+        a = __uint_as_float(r[4 * q + 2]) + bb.z;
+        v[4 * q + 2] = a > 0.f ? a : a * sl.z;
+        a = __uint_as_float(r[4 * q + 3]) + bb.w;
+        v[4 * q + 3] = a > 0.f ? a : a * sl.w;
+      }
+      uint4* s0 = reinterpret_cast<uint4*>(stg + my_row * 128 + (((2 * q4) ^ (my_row & 7)) << 4));
+      uint4* s1 = reinterpret_cast<uint4*>(stg + my_row * 128 + (((2 * q4 + 1) ^ (my_row & 7)) << 4));
+      if (e.res0 != nullptr) {
+        const uint4 ra = *s0, rb = *s1;
+        const uint32_t w[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[2 * j] += e.is_bf16 ? bf16_lo(w[j]) : f16_lo(w[j]);
+          v[2 * j + 1] += e.is_bf16 ? bf16_hi(w[j]) : f16_hi(w[j]);
+        }
+      }
+      uint32_t h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = e.is_bf16 ? pack2<true>(v[2 * j], v[2 * j + 1]) : pack2<false>(v[2 * j], v[2 * j + 1]);
+      *s0 = make_uint4(h[0], h[1], h[2], h[3]);
+      *s1 = make_uint4(h[4], h[5], h[6], h[7]);
+    }
+    __syncwarp();
+    // staging -> global: whole 128-byte pixel rows
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + sub_row;
+      const uint4 q = *reinterpret_cast<const uint4*>(stg + r * 128 + ((chunk ^ (r & 7)) << 4));
+      if ((okmask >> i) & 1u) *reinterpret_cast<uint4*>(optr[i] + c0) = q;
+    }
+    __syncwarp();
+  }
+}
+
 // stage the tile's bias / PReLU slopes in shared memory (called by the 128 epilogue threads)
 __device__ __forceinline__ void stage_bias_slope(float* bs, float* ss, const float* bias, const float* slope, int n0,
                                                  int block_n, int cout, int et) {
@@ -222,7 +331,9 @@ __device__ __forceinline__ void stage_bias_slope(float* bs, float* ss, const flo
 // slab-kernel launcher (conv3x3_slab_sm100.cu); p is fully populated by igemm_launch
 int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream);
 // shared-memory budget of the slab kernel, used by the host to size the rings
-constexpr int SLAB_DATA_BYTES = 208 * 1024;
+constexpr int SLAB_DATA_BYTES = 200 * 1024;   // slab + W rings when the staged epilogue is in use
+constexpr int EPI_STAGING_BYTES = 16 * 1024;  // 4 epilogue warps x [32 rows x 128 B]
+constexpr int SLAB_WRES_BYTES = SLAB_DATA_BYTES + EPI_STAGING_BYTES;   // resident-weight layers (cout < 64) use both
 constexpr int SLAB_TILE_W = 8;    // output tile: 8 wide x 16 tall pixels per accumulator
 constexpr int SLAB_TILE_H = 16;
 

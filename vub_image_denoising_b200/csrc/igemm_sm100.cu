@@ -40,7 +40,8 @@ namespace {
 constexpr int TILE_W = 16;   // accumulator tile of the tap-reload kernel: 16 wide x 8 tall pixels
 constexpr int TILE_H = 8;
 constexpr int RING_BYTES = 192 * 1024;
-constexpr int SMEM_BYTES = 1024 + RING_BYTES + 256 + 2 * 2 * MAX_N * 4;
+constexpr int DATA_BYTES = RING_BYTES + EPI_STAGING_BYTES;   // [A/W ring | epilogue staging]
+constexpr int SMEM_BYTES = 1024 + DATA_BYTES + 256 + 2 * 2 * MAX_N * 4;
 
 // MODE: 0 = CONV3X3 (9 taps, shifted 4-D boxes), 1 = DOWN2X2 (4 taps, 5-D map), 2 = UP2X2 / CONV1X1 (one tap)
 // MT:   A tiles (128 pixels each, x-adjacent) per W tile and pipeline stage.
@@ -56,10 +57,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
-  const uint32_t bars = smem_base + RING_BYTES;
+  const uint32_t bars = smem_base + DATA_BYTES;
   // barrier map: full[8] @0, empty[8] @64, tmem_full[2] @128, tmem_empty[2] @144, tmem ptr @160
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + RING_BYTES + 160);
-  float* epi_bias = reinterpret_cast<float*>(smem_gen + RING_BYTES + 256);  // [2][MAX_N]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + DATA_BYTES + 160);
+  float* epi_bias = reinterpret_cast<float*>(smem_gen + DATA_BYTES + 256);  // [2][MAX_N]
   float* epi_slope = epi_bias + 2 * MAX_N;                                  // [2][MAX_N]
 
   // Role index: hardware warps 4..7 run the single-thread producer / MMA-issue loops, warps 0..3 the epilogue.
@@ -235,6 +236,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     const float* bias = p.bias;
     const float* slope = p.slope;
     const bool up = p.wgroups == 4 && MODE == 2;
+    const bool staged = p.epi_staged;
+    uint8_t* stg = smem_gen + RING_BYTES + we * 4096;
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
       const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
@@ -259,8 +262,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
         }
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n);
-        epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, out_pix, res_pix, t.n0,
-                         j == MT - 1 ? bars + 144 + acc * 8 : 0u);
+        const uint32_t rel = j == MT - 1 ? bars + 144 + acc * 8 : 0u;
+        if (staged) {
+          RowMap rm;
+          rm.b = t.b, rm.y0 = t.y0, rm.x0 = t.x0 + j * TILE_W, rm.tw_shift = 4, rm.H = H, rm.W = W;
+          rm.up = up ? 1 : 0, rm.ky = t.grp >> 1, rm.kx = t.grp & 1;
+          epilogue_subtile_staged(ea, taddr, block_n, bs, ss, rm, we * 32, lane, t.n0, rel, stg);
+        } else {
+          epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, out_pix, res_pix, t.n0, rel);
+        }
       }
     }
   }
@@ -321,6 +331,14 @@ int default_conv3x3_impl() {
     return B200DN_DEFAULT_CONV3X3_IMPL;
   }();
   return impl;
+}
+// B200DN_EPI_STAGED: 0 = never, 1 = whenever legal, 2 = only one-accumulator (MT = 1) tiles
+int staged_mode() {
+  static int mode = [] {
+    const char* e = getenv("B200DN_EPI_STAGED");
+    return e ? atoi(e) : 2;
+  }();
+  return mode;
 }
 bool wres_enabled() {
   static int on = [] {
@@ -432,7 +450,9 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     // small layers: keep the whole packed weight set resident in shared memory (single N tile only)
     p.n_wplanes = two_w ? 2 : 1;
     const int64_t w_all = static_cast<int64_t>(p.n_wplanes) * p.n_cblk * 9 * block_n * 128;
-    p.wres = (p.num_n_tiles == 1 && w_all <= SLAB_DATA_BYTES - p.num_slabs * p.slab_bytes && wres_enabled()) ? 1 : 0;
+    // (cout < 64 only: such layers never use the staged epilogue, so its 16 KB belong to the resident weights)
+    p.wres = (p.num_n_tiles == 1 && block_n < 64 && w_all <= SLAB_WRES_BYTES - p.num_slabs * p.slab_bytes &&
+              wres_enabled()) ? 1 : 0;
   } else {
     p.stage_bytes = mt * A_BYTES + block_n * 128;
     p.num_stages = RING_BYTES / p.stage_bytes;
@@ -445,6 +465,9 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   p.bias = a.bias;
   p.slope = a.slope;
   p.out_kind = a.out_kind;
+  // staged (smem-transposed, 128-byte-row) epilogue: single-plane NHWC output in whole 64-channel groups
+  p.epi_staged = (a.out_kind == B200DN_OUT_NHWC16 && !two_a && block_n % 64 == 0 && a.cout % 64 == 0 &&
+                  a.out_coff % 64 == 0 && a.out_ctot % 8 == 0 && (staged_mode() == 1 || (staged_mode() == 2 && mt == 1))) ? 1 : 0;
   if (a.out_kind == B200DN_OUT_NHWC16) {
     B200DN_CHECK_ARG(a.out[0], "igemm: null NHWC output");
     B200DN_CHECK_ARG(!two_a || a.out[1], "igemm: prec %d needs the lo output plane out[1]", a.prec);

@@ -283,6 +283,7 @@ class ForwardPlan:
         self.signature = None
         self._keep = []          # tensors referenced by raw pointer from the arg blocks
         self.launches = []       # list[IgemmArgs]
+        self.layer_info = []     # per launch: mode / shape / FLOPs (diagnostics)
         self.flops = 0
         dev = self.device
         with torch.cuda.device(dev):
@@ -346,6 +347,8 @@ class ForwardPlan:
         pix = B * H * W if mode != _lib.MODE_DOWN2X2 else B * (H // 2) * (W // 2)
         self.flops += 2 * pix * taps * cin * cout
         self.launches.append(a)
+        self.layer_info.append(dict(mode=mode, H=H, W=W, cin=cin, cout=cout * (4 if transposed else 1),
+                                    flops=2 * pix * taps * cin * cout, nchw=nchw))
         return a
 
     def _dense(self, blk: _Params, src: _Act, dst: _Act, dst_coff: int, B, H, W, C) -> None:
@@ -404,7 +407,8 @@ class ForwardPlan:
 
     # ---- execution
     def run(self, x: torch.Tensor, out: torch.Tensor, t: Optional[torch.Tensor] = None,
-            x_batch: Optional[int] = None, t_strides=None, t_ptr: Optional[int] = None, events=None) -> None:
+            x_batch: Optional[int] = None, t_strides=None, t_ptr: Optional[int] = None, events=None,
+            layer_events=None) -> None:
         """Enqueue one forward on the current stream.
 
         x: fp32 NCHW [Bx, 3, H, W] with Bx = x_batch or B; image b of the network batch reads x[b % Bx]
@@ -437,9 +441,15 @@ class ForwardPlan:
         igemm = lib.b200dn_igemm
         if events is not None:
             events[0].record()
-        for ref in self._refs:
-            rc = igemm(ref, stream)
-            if rc:
-                _lib.check(rc, "igemm")
+        if layer_events is None:
+            for ref in self._refs:
+                rc = igemm(ref, stream)
+                if rc:
+                    _lib.check(rc, "igemm")
+        else:   # diagnostic: one event after every tensor-core launch (tools/layer_times.py)
+            layer_events[0].record()
+            for i, ref in enumerate(self._refs):
+                _lib.check(igemm(ref, stream), "igemm")
+                layer_events[i + 1].record()
         if events is not None:
             events[1].record()
