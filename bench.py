@@ -194,6 +194,14 @@ def run_b200(args) -> None:
         psnr, ssim = b2.metrics.batch_metrics(clean, out, 1.0)    # evaluate_model.py:50-51 convention
         acc.update(psnr, ssim)
 
+    def step_public_api(i: int, src_u8: torch.Tensor) -> torch.Tensor:
+        """The same step through the calls a user of the reference makes: module __call__ + metric functions."""
+        _, noisy, clean = b2.noise.add_gaussian_noise(src_u8, sigma, seed=1000 + i, stream_id=rank, return_u8=False)
+        den = net(noisy)                                           # RDUNet.forward (drop-in nn.Module call)
+        psnr, ssim = b2.metrics.batch_metrics(clean, den, 1.0)
+        acc.update(psnr, ssim)
+        return den
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -220,14 +228,14 @@ def run_b200(args) -> None:
         red = acc.reduce()                                         # ONE all-reduce of (sum psnr, sum ssim, n)
         # ---------------- timed region 2: end to end from pinned host buffers
         for i in range(2):
-            step(i, clean_host.to(dev, non_blocking=True))
+            step_public_api(i, clean_host.to(dev, non_blocking=True))
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for i in range(args.steps):
             src = clean_host.to(dev, non_blocking=True)            # H2D of this step's patches
-            step(i, src)
-            out_host.copy_(out, non_blocking=True)                 # D2H of the denoised batch
+            den = step_public_api(i, src)
+            out_host.copy_(den, non_blocking=True)                 # D2H of the denoised batch
             met_host.copy_(acc.acc, non_blocking=True)             # D2H of the running metric sums
         t1.record()
         barrier()
