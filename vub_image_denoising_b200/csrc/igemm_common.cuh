@@ -319,13 +319,13 @@ __device__ __forceinline__ void epilogue_subtile_staged(const EpiArgs& e, uint32
 
 // stage the tile's bias / PReLU slopes in shared memory (called by the 128 epilogue threads)
 __device__ __forceinline__ void stage_bias_slope(float* bs, float* ss, const float* bias, const float* slope, int n0,
-                                                 int block_n, int cout, int et) {
-  for (int i = et; i < block_n; i += EPI_THREADS) {
+                                                 int block_n, int cout, int et, int n_threads = EPI_THREADS) {
+  for (int i = et; i < block_n; i += n_threads) {
     const int c = n0 + i;
     bs[i] = (c < cout) ? __ldg(bias + c) : 0.f;
     ss[i] = (slope != nullptr && c < cout) ? __ldg(slope + c) : 1.f;
   }
-  asm volatile("bar.sync 1, %0;" ::"r"(EPI_THREADS) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
 }
 
 // slab-kernel launcher (conv3x3_slab_sm100.cu); p is fully populated by igemm_launch

@@ -39,8 +39,9 @@ namespace {
 
 constexpr int TILE_W = 16;   // accumulator tile of the tap-reload kernel: 16 wide x 8 tall pixels
 constexpr int TILE_H = 8;
-constexpr int RING_BYTES = 192 * 1024;
-constexpr int DATA_BYTES = RING_BYTES + EPI_STAGING_BYTES;   // [A/W ring | epilogue staging]
+constexpr int RING_BYTES = 176 * 1024;
+constexpr int TAP_STAGING_BYTES = 32 * 1024;                 // up to 8 epilogue warps x [32 rows x 128 B]
+constexpr int DATA_BYTES = RING_BYTES + TAP_STAGING_BYTES;   // [A/W ring | epilogue staging]
 constexpr int SMEM_BYTES = 1024 + DATA_BYTES + 256 + 2 * 2 * MAX_N * 4;
 
 // MODE: 0 = CONV3X3 (9 taps, shifted 4-D boxes), 1 = DOWN2X2 (4 taps, 5-D map), 2 = UP2X2 / CONV1X1 (one tap)
@@ -51,8 +52,17 @@ constexpr int SMEM_BYTES = 1024 + DATA_BYTES + 256 + 2 * 2 * MAX_N * 4;
 // ncu showed the single-thread issue loops (uniform-datapath instructions at ~5 cycles each), not the
 // tensor pipe, TMA or L2, bound the first version of this kernel (profiles/r01_igemm_v1_n64.txt); hence
 // two producers, two issuers with independent accumulators, and branch-free inner paths.
+// The transposed conv (MODE 2, one accumulator, N = 256) has a short K loop (K = Cin) and a 256-column epilogue:
+// ncu/event timing showed it epilogue-bound, so that variant runs TWO epilogue warp groups (hardware warps 0-3 and
+// 8-11), each draining half of the accumulator's columns.  (For the 3x3 kernels extra epilogue warps were measured
+// to be slower: they take issue slots from the MMA issue loops.)
 template <int MODE, int MT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_constant__ KParams p) {
+constexpr int epi_groups() { return (MODE == 2 && MT == 1) ? 2 : 1; }
+
+template <int MODE, int MT>
+__global__ void __launch_bounds__(NUM_THREADS + EPI_THREADS * (epi_groups<MODE, MT>() - 1), 1)
+igemm_kernel(const __grid_constant__ KParams p) {
+  constexpr int EG = epi_groups<MODE, MT>();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
@@ -81,7 +91,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bars + 128 + a * 8, MT);           // accumulators full: one commit per issuer
-      mbar_init(bars + 144 + a * 8, EPI_THREADS);  // accumulators drained
+      mbar_init(bars + 144 + a * 8, EPI_THREADS * EG);  // accumulators drained (every epilogue thread arrives)
     }
     mbar_fence_init();
   }
@@ -228,16 +238,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
   } else if (warp >= 4) {
     // ======================================================= epilogue
     const int we = warp & 3;  // TMEM lane quarter this warp may access
+    const int eg = (EG == 2 && warp >= 8) ? 1 : 0;   // column half drained by this warp group
     const int row = we * 32 + lane;
     const int th = row / TILE_W, tw = row - th * TILE_W;
-    const int et = threadIdx.x & (EPI_THREADS - 1);   // epilogue threads are hardware threads 0..127
+    const int et = (threadIdx.x & (EPI_THREADS - 1)) + eg * EPI_THREADS;   // hardware threads 0..127 (+ 256..383)
     const EpiArgs ea = make_epi_args(p);
     const int H = p.H, W = p.W, cout = p.cout;
     const float* bias = p.bias;
     const float* slope = p.slope;
     const bool up = p.wgroups == 4 && MODE == 2;
     const bool staged = p.epi_staged;
-    uint8_t* stg = smem_gen + RING_BYTES + we * 4096;
+    uint8_t* stg = smem_gen + RING_BYTES + (eg * 4 + we) * 4096;
+    const int ncols = block_n / EG, col0 = eg * ncols;   // this group's share of the accumulator columns
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
       const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
       const uint32_t acc_phase = (local_tile >> 1) & 1;
       float* bs = epi_bias + acc * MAX_N;
       float* ss = epi_slope + acc * MAX_N;
-      stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et);
+      stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et, EPI_THREADS * EG);
 
       mbar_wait(bars + 128 + acc * 8, acc_phase);
       tc_fence_after();
@@ -261,15 +273,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) igemm_kernel(const __grid_cons
           out_pix = (static_cast<int64_t>(t.b) * (2 * H) + (2 * y + ky)) * (2 * W) + (2 * x + kx);
         }
         const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n);
+            tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n + col0);
         const uint32_t rel = j == MT - 1 ? bars + 144 + acc * 8 : 0u;
         if (staged) {
           RowMap rm;
           rm.b = t.b, rm.y0 = t.y0, rm.x0 = t.x0 + j * TILE_W, rm.tw_shift = 4, rm.H = H, rm.W = W;
           rm.up = up ? 1 : 0, rm.ky = t.grp >> 1, rm.kx = t.grp & 1;
-          epilogue_subtile_staged(ea, taddr, block_n, bs, ss, rm, we * 32, lane, t.n0, rel, stg);
+          epilogue_subtile_staged(ea, taddr, ncols, bs + col0, ss + col0, rm, we * 32, lane, t.n0 + col0, rel, stg);
         } else {
-          epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, out_pix, res_pix, t.n0, rel);
+          epilogue_subtile(ea, taddr, ncols, bs + col0, ss + col0, valid, t.b, y, x, out_pix, res_pix, t.n0 + col0, rel);
         }
       }
     }
@@ -466,7 +478,9 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   p.slope = a.slope;
   p.out_kind = a.out_kind;
   // staged (smem-transposed, 128-byte-row) epilogue: single-plane NHWC output in whole 64-channel groups
-  p.epi_staged = (a.out_kind == B200DN_OUT_NHWC16 && !two_a && block_n % 64 == 0 && a.cout % 64 == 0 &&
+  // (the one-accumulator transposed-conv variant splits the columns over two epilogue groups: 64-channel groups per half)
+  const int epi_cols = (a.mode == B200DN_MODE_UP2X2 && mt == 1) ? block_n / 2 : block_n;
+  p.epi_staged = (a.out_kind == B200DN_OUT_NHWC16 && !two_a && epi_cols % 64 == 0 && a.cout % 64 == 0 &&
                   a.out_coff % 64 == 0 && a.out_ctot % 8 == 0 && (staged_mode() == 1 || (staged_mode() == 2 && mt == 1))) ? 1 : 0;
   if (a.out_kind == B200DN_OUT_NHWC16) {
     B200DN_CHECK_ARG(a.out[0], "igemm: null NHWC output");
@@ -549,7 +563,8 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   });
   if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(igemm_kernel, smem)");
   const int mode_idx = a.mode == B200DN_MODE_CONV3X3 ? 0 : a.mode == B200DN_MODE_DOWN2X2 ? 1 : 2;
-  kernels[mode_idx][mt - 1]<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p);
+  const int threads = NUM_THREADS + ((mode_idx == 2 && mt == 1) ? EPI_THREADS : 0);
+  kernels[mode_idx][mt - 1]<<<grid, threads, SMEM_BYTES, stream>>>(p);
   B200DN_CUDA(cudaGetLastError());
   return 0;
 }
