@@ -36,6 +36,8 @@ int cuda_fail(cudaError_t e, const char* what);   // records + returns B200DN_E_
 // device properties (cached per device); returns <0 on failure
 int device_sm_count();
 int require_sm100();   // 0 if the current device is compute capability 10.x
+// launch a persistent tensor-core kernel, with programmatic stream serialization unless B200DN_PDL=0
+cudaError_t launch_pdl(const void* kernel, int grid, int threads, size_t smem, cudaStream_t stream, void* params);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -114,6 +116,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running.  griddep_wait() blocks until the predecessor grid has
+// completed and its memory is visible; griddep_launch_dependents() lets the successor start its own prologue.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

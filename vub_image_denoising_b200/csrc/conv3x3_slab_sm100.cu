@@ -89,6 +89,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel of
+  // the stream; let the next kernel start its own prologue on idle SMs, then wait for our producer to finish before
+  // any activation memory is touched (packed weights / bias are static and need no wait).
+  griddep_launch_dependents();
+  if (!(WRES && warp == 2)) griddep_wait();
 
   const int num_tiles = p.num_tiles, grid = gridDim.x;
   const int num_n_tiles = p.num_n_tiles, n_tiles_per_group = p.n_tiles_per_group, block_n = p.block_n;
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
                         wp * 9);
       }
       __syncwarp();
+      griddep_wait();
     } else {
     // ===================================================== W-tile TMA producer: one [N x 64] tile per tap
     int ws = 0;
@@ -329,8 +335,9 @@ int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream) {
         g_err = cudaFuncSetAttribute(kernels[m][w], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB);
   });
   if (g_err != cudaSuccess) return cuda_fail(g_err, "cudaFuncSetAttribute(conv3x3_slab_kernel, smem)");
-  kernels[p.mt - 1][p.wres ? 1 : 0]<<<grid, NUM_THREADS, SMEM_BYTES_SLAB, stream>>>(p);
-  B200DN_CUDA(cudaGetLastError());
+  KParams pc = p;
+  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[p.mt - 1][p.wres ? 1 : 0]), grid, NUM_THREADS,
+                         SMEM_BYTES_SLAB, stream, &pc));
   return 0;
 }
 

@@ -103,6 +103,11 @@ igemm_kernel(const __grid_constant__ KParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel of
+  // the stream; let the next kernel start its own prologue on idle SMs, then wait for our producer to finish before
+  // any activation memory is touched (packed weights / bias are static and need no wait).
+  griddep_launch_dependents();
+  griddep_wait();
 
   // Loop-invariant parameters live in registers: every asm volatile("memory") below would otherwise force the
   // compiler to re-read them from the constant bank inside the issue loops.
@@ -564,8 +569,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(igemm_kernel, smem)");
   const int mode_idx = a.mode == B200DN_MODE_CONV3X3 ? 0 : a.mode == B200DN_MODE_DOWN2X2 ? 1 : 2;
   const int threads = NUM_THREADS + ((mode_idx == 2 && mt == 1) ? EPI_THREADS : 0);
-  kernels[mode_idx][mt - 1]<<<grid, threads, SMEM_BYTES, stream>>>(p);
-  B200DN_CUDA(cudaGetLastError());
+  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[mode_idx][mt - 1]), grid, threads, SMEM_BYTES, stream, &p));
   return 0;
 }
 

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <string.h>
+#include <stdlib.h>
 
 namespace b200dn {
 
@@ -65,6 +66,26 @@ int require_sm100() {
     return B200DN_E_CUDA;
   }
   return 0;
+}
+
+cudaError_t launch_pdl(const void* kernel, int grid, int threads, size_t smem, cudaStream_t stream, void* params) {
+  static const int pdl = [] {
+    const char* e = getenv("B200DN_PDL");
+    return e ? atoi(e) : 1;
+  }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  void* args[1] = {params};
+  return cudaLaunchKernelExC(&cfg, kernel, args);
 }
 
 }  // namespace b200dn
