@@ -115,7 +115,7 @@ typedef struct b200dn_igemm_args {
   int32_t block_n;         /* 0 = auto; else UMMA N (multiple of 16, <= 256)         */
   int32_t max_ctas;        /* 0 = one per SM                                         */
   int32_t m_tiles;         /* 0 = auto; 1 or 2 A tiles (128 pixels each) per W tile  */
-  int32_t impl;            /* CONV3X3 only: 0 = default, 1 = per-tap reload, 2 = haloed slab */
+  int32_t impl;            /* CONV3X3 only: 0 = default, 1 = per-tap reload, 2 = haloed slab, 3 = haloed slab on CTA pairs */
 } b200dn_igemm_args;
 
 int b200dn_igemm(const b200dn_igemm_args* args, void* stream);

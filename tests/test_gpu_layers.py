@@ -59,8 +59,8 @@ CONV_CASES = [
 ]
 
 
-IMPLS = [1, 2]
-IMPL_IDS = ["tap", "slab"]
+IMPLS = [1, 2, 3]
+IMPL_IDS = ["tap", "slab", "slab-cta-pair"]   # 3 = cta_group::2 (falls back to the one-CTA slab kernel for N < 32)
 
 
 @pytest.mark.parametrize("impl", IMPLS, ids=IMPL_IDS)

@@ -1,0 +1,327 @@
+// conv3x3_slab2_sm100.cu — the haloed-slab 3x3 convolution (conv3x3_slab_sm100.cu) on CTA PAIRS:
+// `tcgen05.mma.cta_group::2`, M = 256 per instruction (128 pixels per SM), thread-block cluster of 2.
+//
+// Reference op: nn.Conv2d(.,.,3,padding=1) + nn.PReLU (+ residual), UNet/RDUNet_model.py:61,74-75,98-115.
+//
+// Why: with cta_group::1 every UMMA re-reads its whole B operand ([N x 16] weights) from the issuing SM's shared
+// memory, and the N = 64 / 128 layers are bound by shared-memory bandwidth (A 4 KB + B N*32 B per UMMA against
+// ~128 B/clk/SM).  In a CTA pair each SM keeps only HALF of the W tile (rows [r*N/2, (r+1)*N/2))
+// and the hardware shares the halves across the pair, so per SM the W smem reads, the W TMA writes and the
+// L2->SM weight traffic all halve, while each CTA still owns its pixels (slab), its accumulators (TMEM) and its
+// epilogue exactly as in the single-CTA kernel.
+//
+// Protocol (rank 0 = leader):
+//   * both CTAs run the slab producer (warp 0) and the W producer (warp 2) into their OWN shared memory, but every
+//     TMA credits its bytes to the LEADER's full barrier (`.cta_group::2` TMA + mapa address);
+//   * only the leader's issuer warps (1 / 3) issue MMAs; `tcgen05.commit ... multicast::cluster` with mask 0b11
+//     arrives on the empty / accumulator-full barriers at the same offset in BOTH CTAs;
+//   * both epilogues (warps 4..7) drain their own TMEM and release the accumulator stage by a remote arrive on the
+//     leader's barrier (one relaxed arrive per epilogue warp, count = 2 x 4).
+// Tile schedule: pair tile = (two consecutive spatial super tiles, one N tile); clusters take pair tiles round-robin.
+#include "igemm_common.cuh"
+
+#include <mutex>
+
+namespace b200dn {
+namespace igemm {
+
+namespace {
+
+constexpr int TW = SLAB_TILE_W;   // 8
+constexpr int TH = SLAB_TILE_H;   // 16
+constexpr int MAX_SLABS = 3;
+constexpr int DATA_BYTES = SLAB_DATA_BYTES + EPI_STAGING_BYTES;   // [slabs | W ring (half tiles) | epilogue staging]
+constexpr int SMEM_BYTES_SLAB2 = 1024 + DATA_BYTES + 256 + 2 * 2 * MAX_N * 4;
+
+constexpr uint32_t B_SLAB_FULL = 0, B_SLAB_EMPTY = 24, B_W_FULL = 48, B_W_EMPTY = 112, B_TFULL = 176, B_TEMPTY = 192,
+                   B_TMEM_PTR = 208;
+
+// spatial super tile `m_tile` (or an all-out-of-bounds tile past the end, for the odd CTA of the last pair)
+__device__ __forceinline__ TileCoord decode_pair_tile(int pair_tile, int rank, const KParams& p, int tile_w, int tile_h) {
+  TileCoord t;
+  const int m_pair = pair_tile / p.num_n_tiles;
+  const int nt = pair_tile - m_pair * p.num_n_tiles;
+  t.grp = 0;
+  t.n0 = nt * p.block_n;
+  const int m_tile = 2 * m_pair + rank;
+  if (m_tile >= p.num_m_tiles) {
+    t.b = 0, t.x0 = 0, t.y0 = p.tiles_y * tile_h;   // >= H: TMA zero-fills, the epilogue masks every pixel
+    return t;
+  }
+  const int per_img = p.tiles_x * p.tiles_y;
+  t.b = m_tile / per_img;
+  const int r = m_tile - t.b * per_img;
+  const int ty = r / p.tiles_x;
+  t.y0 = ty * tile_h;
+  t.x0 = (r - ty * p.tiles_x) * tile_w;
+  return t;
+}
+
+template <int MT, bool FULLK>
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __grid_constant__ KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
+  const uint32_t bars = smem_base + DATA_BYTES;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + DATA_BYTES + B_TMEM_PTR);
+  float* epi_bias = reinterpret_cast<float*>(smem_gen + DATA_BYTES + 256);  // [2][MAX_N]
+  float* epi_slope = epi_bias + 2 * MAX_N;
+
+  const int warp = (threadIdx.x >> 5) ^ 4;   // hardware warps 4..7 = producers / issuers, 0..3 = epilogue
+  const int lane = threadIdx.x & 31;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmW);
+    if (p.n_pairs > 1) tma_prefetch_desc(&p.tmA1);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < MAX_SLABS; ++s) {
+      mbar_init(bars + B_SLAB_FULL + s * 8, 1);      // leader's: one arrive.expect_tx for both CTAs' bytes
+      mbar_init(bars + B_SLAB_EMPTY + s * 8, MT);    // multicast commits from the leader's issuers
+    }
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(bars + B_W_FULL + s * 8, 1);
+      mbar_init(bars + B_W_EMPTY + s * 8, MT);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bars + B_TFULL + a * 8, MT);
+      mbar_init(bars + B_TEMPTY + a * 8, 2 * (EPI_THREADS / 32));   // leader's: one arrive per epilogue warp of both CTAs
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(smem_u32(tmem_ptr_s), static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits and the TMEM allocation of BOTH CTAs are visible before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  griddep_launch_dependents();
+  griddep_wait();
+
+  const int num_pair_tiles = p.num_tiles;   // pair tiles
+  const int block_n = p.block_n, half_n = p.block_n >> 1;
+  const int n_cblk = p.n_cblk, n_pairs = p.n_pairs;
+  const int num_slabs = p.num_slabs, slab_bytes = p.slab_bytes;
+  const int num_stages = p.num_stages, stage_bytes = p.stage_bytes;
+  const uint32_t wring = smem_base + static_cast<uint32_t>(num_slabs * slab_bytes);
+  constexpr int STH = TH * MT;
+
+  if (warp == 0) {
+    // ===================================================== slab TMA producer (both CTAs, own pixels)
+    int s = 0;
+    uint32_t sph = 0;
+    const int pa0 = p.pair_a[0], pa1 = p.pair_a[1], pa2 = p.pair_a[2];
+    for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters) {
+      const TileCoord t = decode_pair_tile(tile, rank, p, TW, STH);
+      for (int pair = 0; pair < n_pairs; ++pair) {
+        const int pa = pair == 0 ? pa0 : pair == 1 ? pa1 : pa2;
+        const CUtensorMap* tmA = pa ? &p.tmA1 : &p.tmA0;
+        for (int cb = 0; cb < n_cblk; ++cb) {
+          mbar_wait(bars + B_SLAB_EMPTY + s * 8, sph ^ 1u);
+          if (elect_one()) {
+            const uint32_t full = bars + B_SLAB_FULL + s * 8;
+            if (leader) mbar_arrive_expect_tx(full, static_cast<uint32_t>(2 * slab_bytes));
+            tma_load_4d_2sm(smem_base + s * slab_bytes, tmA, mapa_shared(full, 0), cb * BLOCK_K, t.x0 - 1, t.y0 - 1, t.b);
+          }
+          __syncwarp();
+          if (++s == num_slabs) {
+            s = 0;
+            sph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================== W producer (both CTAs): HALF of each [N x 64] tap tile
+    int ws = 0;
+    uint32_t wph = 0;
+    const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128);   // both halves
+    const int pw0 = p.pair_w[0] * 9, pw1 = p.pair_w[1] * 9, pw2 = p.pair_w[2] * 9;
+    for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters) {
+      const TileCoord t = decode_pair_tile(tile, rank, p, TW, STH);
+      const int n_row = t.n0 + rank * half_n;
+      for (int pair = 0; pair < n_pairs; ++pair) {
+        const int wbase = pair == 0 ? pw0 : pair == 1 ? pw1 : pw2;
+        for (int cb = 0; cb < n_cblk; ++cb) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bars + B_W_EMPTY + ws * 8, wph ^ 1u);
+            if (elect_one()) {
+              const uint32_t full = bars + B_W_FULL + ws * 8;
+              if (leader) mbar_arrive_expect_tx(full, w_bytes);
+              tma_load_3d_2sm(wring + ws * stage_bytes, &p.tmW, mapa_shared(full, 0), cb * BLOCK_K, n_row, wbase + tap);
+            }
+            __syncwarp();
+            if (++ws == num_stages) {
+              ws = 0;
+              wph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (leader && (warp == 1 || (warp == 3 && MT == 2))) {
+    // ===================================================== MMA issuer of sub-tile j (leader CTA, drives both SMs)
+    // ONE elected thread runs the whole loop, and the loop is kept small (dy rolled, descriptors and barrier
+    // addresses advanced incrementally): ncu showed this warp issue-bound (~130 SASS instructions per tap with
+    // `no_inst` / `wait` stalls, never waiting for data), which caps the N = 64 layers — 4 UMMAs of 32 clk per tap.
+    {
+      const int j = warp == 1 ? 0 : 1;
+      const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.fmt), static_cast<uint32_t>(block_n), 256u);
+      const int kc_iters = n_pairs * n_cblk;
+      const int last_k16 = p.last_k16;
+      const uint32_t pitch = static_cast<uint32_t>(p.slab_w * 128);   // bytes per slab pixel row = SBO
+      const uint64_t row_step = static_cast<uint64_t>(pitch >> 4);    // descriptor address units (16 B)
+      const uint64_t wdesc0 = make_sw128_desc(wring, 1024);
+      const uint64_t wstep = static_cast<uint64_t>(stage_bytes >> 4);
+      const uint32_t w_full0 = bars + B_W_FULL, w_empty0 = bars + B_W_EMPTY;
+      const uint32_t w_full_end = w_full0 + static_cast<uint32_t>(num_stages) * 8;
+      uint32_t w_full = w_full0, w_empty = w_empty0, wph = 0;
+      uint64_t bdesc = wdesc0;
+      int s = 0;
+      uint32_t sph = 0;
+      int local_tile = 0;
+      for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters, ++local_tile) {
+        const int acc = local_tile & 1;
+        const uint32_t acc_phase = (local_tile >> 1) & 1;
+        mbar_wait(bars + B_TEMPTY + acc * 8, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + static_cast<uint32_t>((acc * MT + j) * block_n);
+        uint32_t accumulate = 0;
+        int cb = 0;
+        for (int kc = 0; kc < kc_iters; ++kc) {
+          const int nk = (FULLK || cb != n_cblk - 1) ? BLOCK_K / 16 : last_k16;
+          mbar_wait(bars + B_SLAB_FULL + s * 8, sph);
+          const uint32_t slab = smem_base + static_cast<uint32_t>(s * slab_bytes) + static_cast<uint32_t>(j * TH) * pitch;
+          uint64_t arow = make_sw128_desc(slab, pitch);
+#pragma unroll 1
+          for (int dy = 0; dy < 3; ++dy, arow += row_step) {
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              mbar_wait(w_full, wph);
+              tc_fence_after();
+              const uint64_t adesc = arow + static_cast<uint64_t>(dx * 8);
+              if (elect_one()) {
+                if (FULLK || nk == BLOCK_K / 16) {
+                  umma_f16_2cta(d, adesc, bdesc, idesc, accumulate);
+                  umma_f16_2cta(d, adesc + 2, bdesc + 2, idesc, 1u);
+                  umma_f16_2cta(d, adesc + 4, bdesc + 4, idesc, 1u);
+                  umma_f16_2cta(d, adesc + 6, bdesc + 6, idesc, 1u);
+                } else {
+#pragma unroll 1
+                  for (int k = 0; k < nk; ++k)
+                    umma_f16_2cta(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? accumulate : 1u);
+                }
+                umma_commit_2cta(w_empty, 3);
+              }
+              __syncwarp();
+              accumulate = 1;
+              w_full += 8, w_empty += 8, bdesc += wstep;
+              if (w_full == w_full_end) {
+                w_full = w_full0, w_empty = w_empty0, bdesc = wdesc0;
+                wph ^= 1u;
+              }
+            }
+          }
+          if (elect_one()) {
+            umma_commit_2cta(bars + B_SLAB_EMPTY + s * 8, 3);                       // both CTAs' slabs consumed
+            if (kc == kc_iters - 1) umma_commit_2cta(bars + B_TFULL + acc * 8, 3);  // both accumulators complete
+          }
+          __syncwarp();
+          if (++s == num_slabs) {
+            s = 0;
+            sph ^= 1u;
+          }
+          if (++cb == n_cblk) cb = 0;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================================= epilogue (both CTAs, own accumulators)
+    const int we = warp & 3;
+    const int row = we * 32 + lane;
+    const int th = row / TW, tw = row - th * TW;
+    const int et = threadIdx.x & (EPI_THREADS - 1);
+    const EpiArgs ea = make_epi_args(p);
+    const int H = p.H, W = p.W, cout = p.cout;
+    const float* bias = p.bias;
+    const float* slope = p.slope;
+    const bool staged = p.epi_staged;
+    uint8_t* stg = smem_gen + SLAB_DATA_BYTES + we * 4096;
+    const uint32_t tempty_leader = mapa_shared(bars + B_TEMPTY, 0);
+    int local_tile = 0;
+    for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters, ++local_tile) {
+      const TileCoord t = decode_pair_tile(tile, rank, p, TW, STH);
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = (local_tile >> 1) & 1;
+      float* bs = epi_bias + acc * MAX_N;
+      float* ss = epi_slope + acc * MAX_N;
+      stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et);
+
+      mbar_wait(bars + B_TFULL + acc * 8, acc_phase);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int j = 0; j < MT; ++j) {
+        const int y = t.y0 + j * TH + th, x = t.x0 + tw;
+        const bool valid = (y < H) && (x < W);
+        const int64_t pix = (static_cast<int64_t>(t.b) * H + y) * W + x;
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n);
+        const uint32_t rel = j == MT - 1 ? tempty_leader + acc * 8 : 0u;
+        if (staged) {
+          RowMap rm;
+          rm.b = t.b, rm.y0 = t.y0 + j * TH, rm.x0 = t.x0, rm.tw_shift = 3, rm.H = H, rm.W = W, rm.up = 0, rm.ky = 0, rm.kx = 0;
+          epilogue_subtile_staged(ea, taddr, block_n, bs, ss, rm, we * 32, lane, t.n0, rel, stg, true);
+        } else {
+          epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, pix, pix, t.n0, rel, true);
+        }
+      }
+    }
+  }
+
+  // Neither CTA may leave (or free its TMEM) while the other can still read its shared memory through an MMA or
+  // signal one of its barriers.
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+std::once_flag g_once;
+cudaError_t g_err = cudaSuccess;
+
+}  // namespace
+
+int launch_conv3x3_slab2(const KParams& p, int grid, cudaStream_t stream) {
+  B200DN_CHECK_ARG(p.cta2 && !p.wres, "conv3x3 slab2: not a CTA-pair configuration");
+  B200DN_CHECK_ARG(p.num_stages >= 2, "conv3x3 slab2: W ring too small for block_n %d", p.block_n);
+  B200DN_CHECK_ARG(p.num_slabs <= MAX_SLABS, "conv3x3 slab2: too many slabs");
+  B200DN_CHECK_ARG(grid >= 2 && grid % 2 == 0, "conv3x3 slab2: grid %d must be a positive multiple of 2", grid);
+  using KernelFn = void (*)(KParams);
+  // FULLK: every 64-channel block is full (cin % 64 == 0), the issue loop needs no per-block k16 count
+  static const KernelFn kernels[2][2] = {{conv3x3_slab2_kernel<1, false>, conv3x3_slab2_kernel<1, true>},
+                                         {conv3x3_slab2_kernel<2, false>, conv3x3_slab2_kernel<2, true>}};
+  std::call_once(g_once, [] {
+    for (int m = 0; m < 2 && g_err == cudaSuccess; ++m)
+      for (int f = 0; f < 2 && g_err == cudaSuccess; ++f)
+        g_err = cudaFuncSetAttribute(kernels[m][f], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB2);
+  });
+  if (g_err != cudaSuccess) return cuda_fail(g_err, "cudaFuncSetAttribute(conv3x3_slab2_kernel, smem)");
+  KParams pc = p;
+  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[p.mt - 1][p.last_k16 == BLOCK_K / 16 ? 1 : 0]), grid,
+                         NUM_THREADS, SMEM_BYTES_SLAB2, stream, &pc, 2));
+  return 0;
+}
+
+}  // namespace igemm
+}  // namespace b200dn

@@ -32,6 +32,7 @@ struct __align__(64) KParams {
   // slab kernel only
   int slab_w, slab_bytes, num_slabs, bo_mode;
   int wres, n_wplanes;   // weights resident in shared memory (small layers)
+  int cta2, num_m_tiles; // CTA-pair kernel (cta_group::2): two spatial super tiles per W tile, one per CTA
   int epi_staged;        // smem-transposed epilogue with 128-byte-row global stores
   const float* bias;
   const float* slope;
@@ -159,14 +160,20 @@ __device__ __forceinline__ void epilogue_nhwc16(const EpiArgs& e, float (&v)[16]
 // `release_bar` != 0: arrive on it right after the last TMEM read (hands the accumulator stage back to the MMA warps).
 __device__ __forceinline__ void epilogue_subtile(const EpiArgs& e, uint32_t taddr, int block_n, const float* bs,
                                                  const float* ss, bool valid, int b, int y, int x, int64_t out_pix,
-                                                 int64_t res_pix, int n0, uint32_t release_bar) {
+                                                 int64_t res_pix, int n0, uint32_t release_bar,
+                                                 bool cluster_rel = false) {
   for (int c0 = 0; c0 < block_n; c0 += 16) {
     uint32_t r[16];
     tmem_ld16(taddr + c0, r);
     tmem_ld_wait();
     if (release_bar != 0 && c0 + 16 >= block_n) {
       tc_fence_before();
-      mbar_arrive(release_bar);
+      if (cluster_rel) {   // CTA pair: the barrier lives in the leader CTA; one remote arrive per warp
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(release_bar);
+      } else {
+        mbar_arrive(release_bar);
+      }
     }
     if (!valid) continue;
     float v[16];
@@ -232,7 +239,8 @@ __device__ __forceinline__ bool row_pixels(const RowMap& m, int row, int64_t& ou
 
 __device__ __forceinline__ void epilogue_subtile_staged(const EpiArgs& e, uint32_t taddr, int block_n, const float* bs,
                                                         const float* ss, const RowMap& m, int row0, int lane, int n0,
-                                                        uint32_t release_bar, uint8_t* stg) {
+                                                        uint32_t release_bar, uint8_t* stg,
+                                                        bool cluster_rel = false) {
   const uint32_t my_row = static_cast<uint32_t>(lane);
   const int sub_row = lane >> 3, chunk = lane & 7;   // coalesced phases: 4 rows x 8 chunks per instruction
   // per-lane addresses of its 8 coalesced rows (invariant over the channel groups of this sub-tile)
@@ -269,7 +277,12 @@ __device__ __forceinline__ void epilogue_subtile_staged(const EpiArgs& e, uint32
       tmem_ld_wait();
       if (release_bar != 0 && c0 + 64 >= block_n && q4 == 3) {
         tc_fence_before();
-        mbar_arrive(release_bar);
+        if (cluster_rel) {
+          __syncwarp();
+          if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(release_bar);
+        } else {
+          mbar_arrive(release_bar);
+        }
       }
       float v[16];
       const float4* b4 = reinterpret_cast<const float4*>(bs + c0 + 16 * q4);
@@ -330,6 +343,8 @@ __device__ __forceinline__ void stage_bias_slope(float* bs, float* ss, const flo
 
 // slab-kernel launcher (conv3x3_slab_sm100.cu); p is fully populated by igemm_launch
 int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream);
+// CTA-pair variant (conv3x3_slab2_sm100.cu); grid = 2 x clusters
+int launch_conv3x3_slab2(const KParams& p, int grid, cudaStream_t stream);
 // shared-memory budget of the slab kernel, used by the host to size the rings
 constexpr int SLAB_DATA_BYTES = 200 * 1024;   // slab + W rings when the staged epilogue is in use
 constexpr int EPI_STAGING_BYTES = 16 * 1024;  // 4 epilogue warps x [32 rows x 128 B]

@@ -364,6 +364,14 @@ bool wres_enabled() {
   }();
   return on != 0;
 }
+// B200DN_CTA2: 0 = never use the CTA-pair slab kernel, 1 = whenever legal and there is enough work (default)
+int cta2_mode() {
+  static int mode = [] {
+    const char* e = getenv("B200DN_CTA2");
+    return e ? atoi(e) : 1;
+  }();
+  return mode;
+}
 int slab_bo_mode() {
   static int mode = [] {
     const char* e = getenv("B200DN_SLAB_BO");
@@ -381,7 +389,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   B200DN_CHECK_ARG(a.in[0] && a.wpacked && a.bias, "igemm: null input/weight/bias pointer");
   B200DN_CHECK_ARG(a.in_ctot % 8 == 0 && a.in_ctot >= a.cin, "igemm: in_ctot %d must be a multiple of 8 and >= cin %d",
                    a.in_ctot, a.cin);
-  B200DN_CHECK_ARG(a.impl >= 0 && a.impl <= 2, "igemm: bad impl %d", a.impl);
+  B200DN_CHECK_ARG(a.impl >= 0 && a.impl <= 3, "igemm: bad impl %d", a.impl);
   const bool two_a = (a.prec == B200DN_PREC_BF16X2 || a.prec == B200DN_PREC_BF16X3 || a.prec == B200DN_PREC_FP16X2);
   const bool two_w = (a.prec == B200DN_PREC_BF16X3);
   B200DN_CHECK_ARG(!two_a || a.in[1], "igemm: prec %d needs the lo activation plane in[1]", a.prec);
@@ -389,7 +397,8 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     B200DN_CHECK_ARG(a.H % 2 == 0 && a.W % 2 == 0, "igemm: DOWN2X2 needs even H, W (got %d x %d)", a.H, a.W);
   if (int rc = require_sm100()) return rc;
   if (int rc = get_encoder()) return rc;
-  const bool slab = a.mode == B200DN_MODE_CONV3X3 && (a.impl ? a.impl : default_conv3x3_impl()) == 2;
+  const int impl = a.impl ? a.impl : default_conv3x3_impl();
+  const bool slab = a.mode == B200DN_MODE_CONV3X3 && impl >= 2;
 
   KParams p;
   memset(&p, 0, sizeof(p));
@@ -437,7 +446,8 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   const int stw = slab ? tw1 : tw1 * mt, sth = slab ? th1 * mt : th1;   // super-tile extent
   p.tiles_x = cdiv(p.W, stw);
   p.tiles_y = cdiv(p.H, sth);
-  p.num_tiles = p.B * p.tiles_x * p.tiles_y * p.num_n_tiles;
+  p.num_m_tiles = p.B * p.tiles_x * p.tiles_y;
+  p.num_tiles = p.num_m_tiles * p.num_n_tiles;
   p.fmt = (a.prec == B200DN_PREC_FP16 || a.prec == B200DN_PREC_FP16X2) ? 0 : 1;
   switch (a.prec) {
     case B200DN_PREC_BF16X2:
@@ -468,8 +478,19 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     p.n_wplanes = two_w ? 2 : 1;
     const int64_t w_all = static_cast<int64_t>(p.n_wplanes) * p.n_cblk * 9 * block_n * 128;
     // (cout < 64 only: such layers never use the staged epilogue, so its 16 KB belong to the resident weights)
-    p.wres = (p.num_n_tiles == 1 && block_n < 64 && w_all <= SLAB_WRES_BYTES - p.num_slabs * p.slab_bytes &&
-              wres_enabled()) ? 1 : 0;
+    p.wres = (impl != 3 && p.num_n_tiles == 1 && block_n < 64 &&
+              w_all <= SLAB_WRES_BYTES - p.num_slabs * p.slab_bytes && wres_enabled()) ? 1 : 0;
+    // CTA pairs (cta_group::2, conv3x3_slab2_sm100.cu): each SM keeps half of every W tile.  Explicit impl 3, or by
+    // default for the streaming-weight layers (N >= 64) when every SM pair still gets at least one pair tile.
+    const int pair_tiles = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
+    p.cta2 = (!p.wres && block_n >= 32 &&
+              (impl == 3 || (a.impl == 0 && cta2_mode() == 1 && block_n >= 64 && pair_tiles >= sms / 2))) ? 1 : 0;
+    if (p.cta2) {
+      p.stage_bytes = (block_n / 2) * 128;                      // this CTA's half of a W tile
+      p.num_stages = (SLAB_DATA_BYTES - p.num_slabs * p.slab_bytes) / p.stage_bytes;
+      if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
+      p.num_tiles = pair_tiles;
+    }
   } else {
     p.stage_bytes = mt * A_BYTES + block_n * 128;
     p.num_stages = RING_BYTES / p.stage_bytes;
@@ -549,12 +570,18 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(cout_pad),
                         static_cast<uint64_t>(p.wgroups) * (two_w ? 2 : 1)};
     uint64_t str[2] = {static_cast<uint64_t>(cin_pad) * 2, static_cast<uint64_t>(cin_pad) * cout_pad * 2};
-    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(block_n), p.wres ? 9u : 1u};   // resident mode: all 9 taps per box
+    // resident mode: all 9 taps per box; CTA pairs: half of the N rows per CTA
+    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.cta2 ? block_n / 2 : block_n), p.wres ? 9u : 1u};
     if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
   }
 
   int grid = p.num_tiles < sms ? p.num_tiles : sms;
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
+  if (slab && p.cta2) {
+    int clusters = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
+    if (a.max_ctas > 0 && clusters > (a.max_ctas + 1) / 2) clusters = (a.max_ctas + 1) / 2;
+    return launch_conv3x3_slab2(p, 2 * clusters, stream);
+  }
   if (slab) return launch_conv3x3_slab(p, grid, stream);
 
   using KernelFn = void (*)(KParams);

@@ -68,7 +68,8 @@ int require_sm100() {
   return 0;
 }
 
-cudaError_t launch_pdl(const void* kernel, int grid, int threads, size_t smem, cudaStream_t stream, void* params) {
+cudaError_t launch_pdl(const void* kernel, int grid, int threads, size_t smem, cudaStream_t stream, void* params,
+                       int cluster) {
   static const int pdl = [] {
     const char* e = getenv("B200DN_PDL");
     return e ? atoi(e) : 1;
@@ -79,11 +80,22 @@ cudaError_t launch_pdl(const void* kernel, int grid, int threads, size_t smem, c
   cfg.blockDim = dim3(static_cast<unsigned>(threads));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = n;
   void* args[1] = {params};
   return cudaLaunchKernelExC(&cfg, kernel, args);
 }
