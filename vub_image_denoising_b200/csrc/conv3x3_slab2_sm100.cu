@@ -29,12 +29,13 @@ namespace {
 
 constexpr int TW = SLAB_TILE_W;   // 8
 constexpr int TH = SLAB_TILE_H;   // 16
-constexpr int MAX_SLABS = 3;
+constexpr int MAX_SLABS = SLAB_MAX_SLABS;
 constexpr int DATA_BYTES = SLAB_DATA_BYTES + EPI_STAGING_BYTES;   // [slabs | W ring (half tiles) | epilogue staging]
-constexpr int SMEM_BYTES_SLAB2 = 1024 + DATA_BYTES + 256 + 2 * 2 * MAX_N * 4;
+constexpr int SMEM_BYTES_SLAB2 = 1024 + DATA_BYTES + SLAB_CTRL_BYTES + 2 * 2 * MAX_N * 4;
 
-constexpr uint32_t B_SLAB_FULL = 0, B_SLAB_EMPTY = 24, B_W_FULL = 48, B_W_EMPTY = 112, B_TFULL = 176, B_TEMPTY = 192,
-                   B_TMEM_PTR = 208;
+// barrier map (byte offsets from `bars`): up to 8 slab slots and 8 W stages
+constexpr uint32_t B_SLAB_FULL = 0, B_SLAB_EMPTY = 64, B_W_FULL = 128, B_W_EMPTY = 192, B_TFULL = 256, B_TEMPTY = 272,
+                   B_TMEM_PTR = 288;
 
 // spatial super tile `m_tile` (or an all-out-of-bounds tile past the end, for the odd CTA of the last pair)
 __device__ __forceinline__ TileCoord decode_pair_tile(int pair_tile, int rank, const KParams& p, int tile_w, int tile_h) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ TileCoord decode_pair_tile(int pair_tile, int rank, c
   return t;
 }
 
-template <int MT, bool FULLK>
+template <int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
   uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
   const uint32_t bars = smem_base + DATA_BYTES;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + DATA_BYTES + B_TMEM_PTR);
-  float* epi_bias = reinterpret_cast<float*>(smem_gen + DATA_BYTES + 256);  // [2][MAX_N]
+  float* epi_bias = reinterpret_cast<float*>(smem_gen + DATA_BYTES + SLAB_CTRL_BYTES);  // [2][MAX_N]
   float* epi_slope = epi_bias + 2 * MAX_N;
 
   const int warp = (threadIdx.x >> 5) ^ 4;   // hardware warps 4..7 = producers / issuers, 0..3 = epilogue
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
           mbar_wait(bars + B_SLAB_EMPTY + s * 8, sph ^ 1u);
           if (elect_one()) {
             const uint32_t full = bars + B_SLAB_FULL + s * 8;
-            if (leader) mbar_arrive_expect_tx(full, static_cast<uint32_t>(2 * slab_bytes));
+            if (leader) mbar_arrive_expect_tx(full, static_cast<uint32_t>(2 * p.slab_tx));
             tma_load_4d_2sm(smem_base + s * slab_bytes, tmA, mapa_shared(full, 0), cb * BLOCK_K, t.x0 - 1, t.y0 - 1, t.b);
           }
           __syncwarp();
@@ -169,9 +170,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
     }
   } else if (leader && (warp == 1 || (warp == 3 && MT == 2))) {
     // ===================================================== MMA issuer of sub-tile j (leader CTA, drives both SMs)
-    // ONE elected thread runs the whole loop, and the loop is kept small (dy rolled, descriptors and barrier
-    // addresses advanced incrementally): ncu showed this warp issue-bound (~130 SASS instructions per tap with
-    // `no_inst` / `wait` stalls, never waiting for data), which caps the N = 64 layers — 4 UMMAs of 32 clk per tap.
+    // The loop is kept small (dy rolled, descriptors and barrier addresses advanced incrementally, k16 count a
+    // compile-time constant per 9-tap block): ncu showed this warp issue-bound (~130 SASS instructions per tap with
+    // `no_inst` / `wait` stalls, never waiting for data), which capped the N = 64 layers — 4 UMMAs of 32 clk per tap.
     {
       const int j = warp == 1 ? 0 : 1;
       const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.fmt), static_cast<uint32_t>(block_n), 256u);
@@ -179,12 +180,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
       const int last_k16 = p.last_k16;
       const uint32_t pitch = static_cast<uint32_t>(p.slab_w * 128);   // bytes per slab pixel row = SBO
       const uint64_t row_step = static_cast<uint64_t>(pitch >> 4);    // descriptor address units (16 B)
-      const uint64_t wdesc0 = make_sw128_desc(wring, 1024);
-      const uint64_t wstep = static_cast<uint64_t>(stage_bytes >> 4);
-      const uint32_t w_full0 = bars + B_W_FULL, w_empty0 = bars + B_W_EMPTY;
-      const uint32_t w_full_end = w_full0 + static_cast<uint32_t>(num_stages) * 8;
-      uint32_t w_full = w_full0, w_empty = w_empty0, wph = 0;
-      uint64_t bdesc = wdesc0;
+      WRing wr;
+      wr.full0 = bars + B_W_FULL, wr.empty0 = bars + B_W_EMPTY;
+      wr.full_end = wr.full0 + static_cast<uint32_t>(num_stages) * 8;
+      wr.desc0 = make_sw128_desc(wring, 1024);
+      wr.step = static_cast<uint64_t>(stage_bytes >> 4);
+      wr.full = wr.full0, wr.empty = wr.empty0, wr.phase = 0, wr.desc = wr.desc0;
       int s = 0;
       uint32_t sph = 0;
       int local_tile = 0;
@@ -197,38 +198,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
         uint32_t accumulate = 0;
         int cb = 0;
         for (int kc = 0; kc < kc_iters; ++kc) {
-          const int nk = (FULLK || cb != n_cblk - 1) ? BLOCK_K / 16 : last_k16;
+          const int nk = (cb != n_cblk - 1) ? BLOCK_K / 16 : last_k16;
           mbar_wait(bars + B_SLAB_FULL + s * 8, sph);
           const uint32_t slab = smem_base + static_cast<uint32_t>(s * slab_bytes) + static_cast<uint32_t>(j * TH) * pitch;
           uint64_t arow = make_sw128_desc(slab, pitch);
-#pragma unroll 1
-          for (int dy = 0; dy < 3; ++dy, arow += row_step) {
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              mbar_wait(w_full, wph);
-              tc_fence_after();
-              const uint64_t adesc = arow + static_cast<uint64_t>(dx * 8);
-              if (elect_one()) {
-                if (FULLK || nk == BLOCK_K / 16) {
-                  umma_f16_2cta(d, adesc, bdesc, idesc, accumulate);
-                  umma_f16_2cta(d, adesc + 2, bdesc + 2, idesc, 1u);
-                  umma_f16_2cta(d, adesc + 4, bdesc + 4, idesc, 1u);
-                  umma_f16_2cta(d, adesc + 6, bdesc + 6, idesc, 1u);
-                } else {
-#pragma unroll 1
-                  for (int k = 0; k < nk; ++k)
-                    umma_f16_2cta(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? accumulate : 1u);
-                }
-                umma_commit_2cta(w_empty, 3);
-              }
-              __syncwarp();
-              accumulate = 1;
-              w_full += 8, w_empty += 8, bdesc += wstep;
-              if (w_full == w_full_end) {
-                w_full = w_full0, w_empty = w_empty0, bdesc = wdesc0;
-                wph ^= 1u;
-              }
-            }
+          switch (nk) {   // one dispatch per 9 taps; inside, the k16 count is a compile-time constant
+            case 4: issue_slab_block_streamed<4, true>(d, arow, row_step, wr, idesc, accumulate); break;
+            case 3: issue_slab_block_streamed<3, true>(d, arow, row_step, wr, idesc, accumulate); break;
+            case 2: issue_slab_block_streamed<2, true>(d, arow, row_step, wr, idesc, accumulate); break;
+            default: issue_slab_block_streamed<1, true>(d, arow, row_step, wr, idesc, accumulate); break;
           }
           if (elect_one()) {
             umma_commit_2cta(bars + B_SLAB_EMPTY + s * 8, 3);                       // both CTAs' slabs consumed
@@ -308,18 +286,15 @@ int launch_conv3x3_slab2(const KParams& p, int grid, cudaStream_t stream) {
   B200DN_CHECK_ARG(p.num_slabs <= MAX_SLABS, "conv3x3 slab2: too many slabs");
   B200DN_CHECK_ARG(grid >= 2 && grid % 2 == 0, "conv3x3 slab2: grid %d must be a positive multiple of 2", grid);
   using KernelFn = void (*)(KParams);
-  // FULLK: every 64-channel block is full (cin % 64 == 0), the issue loop needs no per-block k16 count
-  static const KernelFn kernels[2][2] = {{conv3x3_slab2_kernel<1, false>, conv3x3_slab2_kernel<1, true>},
-                                         {conv3x3_slab2_kernel<2, false>, conv3x3_slab2_kernel<2, true>}};
+  static const KernelFn kernels[2] = {conv3x3_slab2_kernel<1>, conv3x3_slab2_kernel<2>};
   std::call_once(g_once, [] {
     for (int m = 0; m < 2 && g_err == cudaSuccess; ++m)
-      for (int f = 0; f < 2 && g_err == cudaSuccess; ++f)
-        g_err = cudaFuncSetAttribute(kernels[m][f], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB2);
+      g_err = cudaFuncSetAttribute(kernels[m], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB2);
   });
   if (g_err != cudaSuccess) return cuda_fail(g_err, "cudaFuncSetAttribute(conv3x3_slab2_kernel, smem)");
   KParams pc = p;
-  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[p.mt - 1][p.last_k16 == BLOCK_K / 16 ? 1 : 0]), grid,
-                         NUM_THREADS, SMEM_BYTES_SLAB2, stream, &pc, 2));
+  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[p.mt - 1]), grid, NUM_THREADS, SMEM_BYTES_SLAB2, stream,
+                         &pc, 2));
   return 0;
 }
 

@@ -28,17 +28,14 @@ namespace {
 
 constexpr int TW = SLAB_TILE_W;   // 8
 constexpr int TH = SLAB_TILE_H;   // 16
-constexpr int MAX_SLABS = 3;
+constexpr int MAX_SLABS = SLAB_MAX_SLABS;
 constexpr int DATA_BYTES = SLAB_DATA_BYTES + EPI_STAGING_BYTES;   // [slabs | W ring or resident W | epilogue staging]
-constexpr int SMEM_BYTES_SLAB = 1024 + DATA_BYTES + 256 + 2 * 2 * MAX_N * 4;
+constexpr int SMEM_BYTES_SLAB = 1024 + DATA_BYTES + SLAB_CTRL_BYTES + 2 * 2 * MAX_N * 4;
 
 // barrier map (byte offsets from `bars`)
-constexpr uint32_t B_SLAB_FULL = 0, B_SLAB_EMPTY = 24, B_W_FULL = 48, B_W_EMPTY = 112, B_TFULL = 176, B_TEMPTY = 192,
-                   B_TMEM_PTR = 208;
-
-__device__ __forceinline__ uint64_t make_sw128_desc_bo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_off) {
-  return make_sw128_desc(smem_addr, sbo_bytes) | (static_cast<uint64_t>(base_off & 7u) << 49);
-}
+// barrier map (byte offsets from `bars`): up to 8 slab slots and 8 W stages
+constexpr uint32_t B_SLAB_FULL = 0, B_SLAB_EMPTY = 64, B_W_FULL = 128, B_W_EMPTY = 192, B_TFULL = 256, B_TEMPTY = 272,
+                   B_TMEM_PTR = 288;
 
 // WRES: the layer's whole packed weight set ([w plane][64-ch block][tap][N x 64]) is loaded into shared memory once
 // per CTA and stays resident; the main loop then only streams slabs.  Used for the small layers (F = 32 levels 0/1),
@@ -52,7 +49,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
   uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
   const uint32_t bars = smem_base + DATA_BYTES;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + DATA_BYTES + B_TMEM_PTR);
-  float* epi_bias = reinterpret_cast<float*>(smem_gen + DATA_BYTES + 256);  // [2][MAX_N]
+  float* epi_bias = reinterpret_cast<float*>(smem_gen + DATA_BYTES + SLAB_CTRL_BYTES);  // [2][MAX_N]
   float* epi_slope = epi_bias + 2 * MAX_N;
 
   // Role index: hardware warps 4..7 run the single-thread producer / MMA-issue loops, warps 0..3 the epilogue.
@@ -118,7 +115,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
           mbar_wait(bars + B_SLAB_EMPTY + s * 8, sph ^ 1u);
           if (elect_one()) {
             const uint32_t full = bars + B_SLAB_FULL + s * 8;
-            mbar_arrive_expect_tx(full, static_cast<uint32_t>(slab_bytes));
+            mbar_arrive_expect_tx(full, static_cast<uint32_t>(p.slab_tx));
             tma_load_4d(smem_base + s * slab_bytes, tmA, full, cb * BLOCK_K, t.x0 - 1, t.y0 - 1, t.b);
           }
           __syncwarp();
@@ -175,49 +172,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
     }
   } else if (warp == 1 || (warp == 3 && MT == 2)) {
     // ===================================================== MMA issuer of sub-tile j
+    // The loop is deliberately small: dy rolled, descriptors and barrier addresses advanced incrementally, the k16
+    // count of a tap a compile-time constant per code path.  ncu (profiles/r01_n64_issuer_warp_issue_bound_ncu.txt)
+    // showed this warp issue-bound — ~130 SASS instructions per tap, never waiting for data — which capped every
+    // layer with N <= 64.
     const int j = warp == 1 ? 0 : 1;
     const uint32_t idesc = make_idesc_f16(static_cast<uint32_t>(p.fmt), static_cast<uint32_t>(block_n));
     const int kc_iters = n_pairs * n_cblk;
     const int last_k16 = p.last_k16;
     const uint32_t pitch = static_cast<uint32_t>(p.slab_w * 128);   // bytes per slab pixel row = SBO
-    const uint32_t bo_mode = static_cast<uint32_t>(p.bo_mode);
+    const uint64_t row_step = static_cast<uint64_t>(pitch >> 4);    // descriptor address units (16 B)
     const int pw_0 = p.pair_w[0], pw_1 = p.pair_w[1], pw_2 = p.pair_w[2];
     const uint32_t w_tile_bytes = static_cast<uint32_t>(block_n * 128);
+    // streamed-W ring cursor (unused when the weights are resident)
+    WRing wr;
+    wr.full0 = bars + B_W_FULL, wr.empty0 = bars + B_W_EMPTY;
+    wr.full_end = wr.full0 + static_cast<uint32_t>(num_stages) * 8;
+    wr.desc0 = make_sw128_desc(wring, 1024);
+    wr.step = static_cast<uint64_t>(stage_bytes >> 4);
+    wr.full = wr.full0, wr.empty = wr.empty0, wr.phase = 0, wr.desc = wr.desc0;
+    const uint64_t bstep = static_cast<uint64_t>(w_tile_bytes >> 4);
     if (WRES) mbar_wait(bars + B_W_FULL, 0);   // resident weights have landed
-    int s = 0, ws = 0;
-    uint32_t sph = 0, wph = 0;
+    int s = 0;
+    uint32_t sph = 0;
     int local_tile = 0;
-    uint32_t ready = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (local_tile >> 1) & 1;
       mbar_wait(bars + B_TEMPTY + acc * 8, acc_phase ^ 1u);
+      tc_fence_after();
       const uint32_t d = tmem_base + static_cast<uint32_t>((acc * MT + j) * block_n);
       uint32_t accumulate = 0;
       int cb = 0;
       for (int kc = 0; kc < kc_iters; ++kc) {
-        const bool full_block = (cb != n_cblk - 1) || (last_k16 == BLOCK_K / 16);
+        const int nk = (cb != n_cblk - 1) ? BLOCK_K / 16 : last_k16;
         mbar_wait(bars + B_SLAB_FULL + s * 8, sph);
+        tc_fence_after();
         const uint32_t slab = smem_base + static_cast<uint32_t>(s * slab_bytes) + static_cast<uint32_t>(j * TH) * pitch;
+        uint64_t arow = make_sw128_desc(slab, pitch);
         if (WRES) {
           // resident weights: [w plane][cb][tap][N x 64]; pair index = kc / n_cblk
           const int pair = kc / n_cblk;
           const int wpl = pair == 0 ? pw_0 : pair == 1 ? pw_1 : pw_2;
-          const uint32_t w_cb = wring + static_cast<uint32_t>((wpl * n_cblk + cb) * 9) * w_tile_bytes;
-          tc_fence_after();
+          const uint64_t bdesc = make_sw128_desc(wring + static_cast<uint32_t>((wpl * n_cblk + cb) * 9) * w_tile_bytes, 1024);
           if (elect_one()) {
-            const int nk = full_block ? BLOCK_K / 16 : last_k16;
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-              const int dy = tap / 3, dx = tap - dy * 3;
-              const uint32_t a_addr = slab + static_cast<uint32_t>(dy) * pitch + static_cast<uint32_t>(dx * 128);
-              const uint64_t adesc = make_sw128_desc(a_addr, pitch);
-              const uint64_t bdesc = make_sw128_desc(w_cb + static_cast<uint32_t>(tap) * w_tile_bytes, 1024);
-#pragma unroll 1
-              for (int k = 0; k < nk; ++k) {
-                umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, accumulate);
-                accumulate = 1;
-              }
+            switch (nk) {   // one dispatch per 9 taps; inside, the k16 count is a compile-time constant
+              case 4: issue_slab_block_resident<4>(d, arow, row_step, bdesc, bstep, idesc, accumulate); break;
+              case 3: issue_slab_block_resident<3>(d, arow, row_step, bdesc, bstep, idesc, accumulate); break;
+              case 2: issue_slab_block_resident<2>(d, arow, row_step, bdesc, bstep, idesc, accumulate); break;
+              default: issue_slab_block_resident<1>(d, arow, row_step, bdesc, bstep, idesc, accumulate); break;
             }
             umma_commit(bars + B_SLAB_EMPTY + s * 8);
             if (kc == kc_iters - 1) umma_commit(bars + B_TFULL + acc * 8);
@@ -225,40 +228,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
           __syncwarp();
           accumulate = 1;
         } else {
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3, dx = tap % 3;
-          if (!ready) mbar_wait(bars + B_W_FULL + ws * 8, wph);
-          tc_fence_after();
-          const uint32_t w_addr = wring + ws * stage_bytes;
-          const uint32_t w_empty = bars + B_W_EMPTY + ws * 8;
-          if (++ws == num_stages) {
-            ws = 0;
-            wph ^= 1u;
+          switch (nk) {
+            case 4: issue_slab_block_streamed<4, false>(d, arow, row_step, wr, idesc, accumulate); break;
+            case 3: issue_slab_block_streamed<3, false>(d, arow, row_step, wr, idesc, accumulate); break;
+            case 2: issue_slab_block_streamed<2, false>(d, arow, row_step, wr, idesc, accumulate); break;
+            default: issue_slab_block_streamed<1, false>(d, arow, row_step, wr, idesc, accumulate); break;
           }
-          ready = mbar_test_wait(bars + B_W_FULL + ws * 8, wph);   // peek at the next W tile
           if (elect_one()) {
-            const uint32_t a_addr = slab + static_cast<uint32_t>(dy) * pitch + static_cast<uint32_t>(dx * 128);
-            const uint64_t adesc = make_sw128_desc_bo(a_addr, pitch, bo_mode ? (a_addr >> 7) : 0u);
-            const uint64_t bdesc = make_sw128_desc(w_addr, 1024);
-            if (full_block) {
-              umma_f16(d, adesc, bdesc, idesc, accumulate);
-              umma_f16(d, adesc + 2, bdesc + 2, idesc, 1u);
-              umma_f16(d, adesc + 4, bdesc + 4, idesc, 1u);
-              umma_f16(d, adesc + 6, bdesc + 6, idesc, 1u);
-            } else {
-              for (int k = 0; k < last_k16; ++k)
-                umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? accumulate : 1u);
-            }
-            umma_commit(w_empty);
-            if (tap == 8) {
-              umma_commit(bars + B_SLAB_EMPTY + s * 8);                         // slab consumed by all 9 taps
-              if (kc == kc_iters - 1) umma_commit(bars + B_TFULL + acc * 8);    // accumulator complete
-            }
+            umma_commit(bars + B_SLAB_EMPTY + s * 8);                         // slab consumed by all 9 taps
+            if (kc == kc_iters - 1) umma_commit(bars + B_TFULL + acc * 8);    // accumulator complete
           }
           __syncwarp();
-          accumulate = 1;
-        }
         }
         if (++s == num_slabs) {
           s = 0;

@@ -30,7 +30,8 @@ struct __align__(64) KParams {
   int fmt;  // 1 bf16, 0 fp16
   int num_stages, stage_bytes, tmem_cols;
   // slab kernel only
-  int slab_w, slab_bytes, num_slabs, bo_mode;
+  int slab_w, slab_bytes, num_slabs, bo_mode;   // slab_bytes = ring slot stride (1 KB multiple)
+  int slab_tx;                                  // bytes one slab TMA box delivers
   int wres, n_wplanes;   // weights resident in shared memory (small layers)
   int cta2, num_m_tiles; // CTA-pair kernel (cta_group::2): two spatial super tiles per W tile, one per CTA
   int epi_staged;        // smem-transposed epilogue with 128-byte-row global stores
@@ -341,6 +342,73 @@ __device__ __forceinline__ void stage_bias_slope(float* bs, float* ss, const flo
   asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
 }
 
+// NK consecutive k16 steps of one filter tap: D (+)= A[128 x 16] * B[N x 16]^T, descriptors advanced by 32 B (2 units).
+// Compile-time NK keeps the single-thread issue loop straight-line (3 SASS instructions per UMMA); ncu had shown the
+// issuer warp, not the data, limiting the small-N layers.
+template <int NK, bool CTA2>
+__device__ __forceinline__ void issue_k16_steps(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    if (CTA2)
+      umma_f16_2cta(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? accumulate : 1u);
+    else
+      umma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc, k == 0 ? accumulate : 1u);
+  }
+}
+// Streamed-W ring cursor of an MMA issuer: barrier addresses and the B descriptor advance together.
+struct WRing {
+  uint32_t full, empty, phase;
+  uint64_t desc;
+  uint32_t full0, empty0, full_end;
+  uint64_t desc0, step;
+  __device__ __forceinline__ void advance() {
+    full += 8, empty += 8, desc += step;
+    if (full == full_end) {
+      full = full0, empty = empty0, desc = desc0;
+      phase ^= 1u;
+    }
+  }
+};
+
+// The 9 taps of one 64-channel block of a slab, weights streamed through the ring: per tap wait for the W tile,
+// issue NK UMMAs, commit the stage back to the W producer.  `arow` = descriptor of the slab row of tap (0, 0).
+template <int NK, bool CTA2>
+__device__ __forceinline__ void issue_slab_block_streamed(uint32_t d, uint64_t arow, uint64_t row_step, WRing& w,
+                                                          uint32_t idesc, uint32_t& accumulate) {
+#pragma unroll 1
+  for (int dy = 0; dy < 3; ++dy, arow += row_step) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      mbar_wait(w.full, w.phase);
+      tc_fence_after();
+      if (elect_one()) {
+        issue_k16_steps<NK, CTA2>(d, arow + static_cast<uint64_t>(dx * 8), w.desc, idesc, accumulate);
+        if (CTA2)
+          umma_commit_2cta(w.empty, 3);
+        else
+          umma_commit(w.empty);
+      }
+      __syncwarp();
+      accumulate = 1;
+      w.advance();
+    }
+  }
+}
+// Same with the weights resident in shared memory ([tap][N x 64] tiles `bstep` apart); called by ONE elected thread.
+template <int NK>
+__device__ __forceinline__ void issue_slab_block_resident(uint32_t d, uint64_t arow, uint64_t row_step, uint64_t bdesc,
+                                                          uint64_t bstep, uint32_t idesc, uint32_t accumulate) {
+#pragma unroll 1
+  for (int dy = 0; dy < 3; ++dy, arow += row_step) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx, bdesc += bstep) {
+      issue_k16_steps<NK, false>(d, arow + static_cast<uint64_t>(dx * 8), bdesc, idesc, accumulate);
+      accumulate = 1;
+    }
+  }
+}
+
 // slab-kernel launcher (conv3x3_slab_sm100.cu); p is fully populated by igemm_launch
 int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream);
 // CTA-pair variant (conv3x3_slab2_sm100.cu); grid = 2 x clusters
@@ -349,6 +417,8 @@ int launch_conv3x3_slab2(const KParams& p, int grid, cudaStream_t stream);
 constexpr int SLAB_DATA_BYTES = 200 * 1024;   // slab + W rings when the staged epilogue is in use
 constexpr int EPI_STAGING_BYTES = 16 * 1024;  // 4 epilogue warps x [32 rows x 128 B]
 constexpr int SLAB_WRES_BYTES = SLAB_DATA_BYTES + EPI_STAGING_BYTES;   // resident-weight layers (cout < 64) use both
+constexpr int SLAB_MAX_SLABS = 6;              // slab ring depth limit (barrier map has room for 8)
+constexpr int SLAB_CTRL_BYTES = 384;           // mbarriers + TMEM pointer, ahead of the staged bias / slopes
 constexpr int SLAB_TILE_W = 8;    // output tile: 8 wide x 16 tall pixels per accumulator
 constexpr int SLAB_TILE_H = 16;
 

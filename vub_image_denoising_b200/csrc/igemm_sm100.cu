@@ -320,10 +320,11 @@ int get_encoder() {
 }
 
 int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const uint64_t* dims,
-           const uint64_t* strides_bytes, const uint32_t* box, const char* what) {
+           const uint64_t* strides_bytes, const uint32_t* box, const char* what,
+           CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B) {
   uint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(tm, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), dims, strides_bytes, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (rank %d dims %llu %llu %llu %llu %llu)", what,
@@ -372,12 +373,23 @@ int cta2_mode() {
   }();
   return mode;
 }
-int slab_bo_mode() {
-  static int mode = [] {
-    const char* e = getenv("B200DN_SLAB_BO");
-    return e ? atoi(e) : 0;   // measured on B200: the swizzle XOR uses absolute smem address bits, base offset stays 0
+// B200DN_SLAB_PITCH: slab row pitch in pixels, 10 (default) .. 16 (the first version's layout)
+int slab_pitch() {
+  static int w = [] {
+    const char* e = getenv("B200DN_SLAB_PITCH");
+    const int v = e ? atoi(e) : 10;
+    return v < 10 ? 10 : v > 16 ? 16 : v;
   }();
-  return mode;
+  return w;
+}
+// B200DN_L2PROMO: L2 promotion of the activation tensor maps, 0 none / 1 64 B / 2 128 B / 3 256 B
+CUtensorMapL2promotion a_l2_promotion() {
+  static int v = [] {
+    const char* e = getenv("B200DN_L2PROMO");
+    return e ? atoi(e) : 3;
+  }();
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+       : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 }
 
 }  // namespace
@@ -467,30 +479,41 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
       p.pair_w[0] = 0, p.pair_a[0] = 0;
   }
   if (slab) {
-    p.slab_w = 16;                                              // slab row pitch in pixels: SBO = 16 * 128 B
-    p.slab_bytes = p.slab_w * (SLAB_TILE_H * mt + 2) * 128;     // 36 KB (mt 1) / 68 KB (mt 2), multiples of 1 KB
-    p.num_slabs = (mt == 1 && block_n <= 128) ? 3 : 2;         // N = 256: trade a slab for a 4th W stage
-    p.stage_bytes = block_n * 128;                              // W ring stage
-    p.num_stages = (SLAB_DATA_BYTES - p.num_slabs * p.slab_bytes) / p.stage_bytes;
-    if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
-    p.bo_mode = slab_bo_mode();
-    // small layers: keep the whole packed weight set resident in shared memory (single N tile only)
+    // Slab row pitch in pixels (SBO = pitch * 128 B).  The 8-wide tile needs 10 (one halo pixel each side); the swizzle
+    // XOR of TMA and UMMA follows absolute shared-memory address bits, so the pitch need not be a multiple of the
+    // 8-row swizzle atom.  10 instead of 16 cuts the slab's L2->SM bytes and shared-memory writes by 37.5 % and makes
+    // room for a deeper ring (more loads in flight per SM; the F = 32 level-0 layers were waiting on slab data).
+    p.slab_w = slab_pitch();
+    p.slab_tx = p.slab_w * (SLAB_TILE_H * mt + 2) * 128;
+    p.slab_bytes = round_up(p.slab_tx, 1024);
+    p.bo_mode = 0;
     p.n_wplanes = two_w ? 2 : 1;
     const int64_t w_all = static_cast<int64_t>(p.n_wplanes) * p.n_cblk * 9 * block_n * 128;
-    // (cout < 64 only: such layers never use the staged epilogue, so its 16 KB belong to the resident weights)
-    p.wres = (impl != 3 && p.num_n_tiles == 1 && block_n < 64 &&
-              w_all <= SLAB_WRES_BYTES - p.num_slabs * p.slab_bytes && wres_enabled()) ? 1 : 0;
+    // small layers: keep the whole packed weight set resident in shared memory (single N tile only; cout < 64: such
+    // layers never use the staged epilogue, so its 16 KB belong to the resident weights) next to >= 2 slabs
+    p.wres = (impl != 3 && p.num_n_tiles == 1 && block_n < 64 && w_all <= SLAB_WRES_BYTES - 2 * p.slab_bytes &&
+              wres_enabled()) ? 1 : 0;
     // CTA pairs (cta_group::2, conv3x3_slab2_sm100.cu): each SM keeps half of every W tile.  Explicit impl 3, or by
     // default for the streaming-weight layers (N >= 64) when every SM pair still gets at least one pair tile.
     const int pair_tiles = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
     p.cta2 = (!p.wres && block_n >= 32 &&
               (impl == 3 || (a.impl == 0 && cta2_mode() == 1 && block_n >= 64 && pair_tiles >= sms / 2))) ? 1 : 0;
-    if (p.cta2) {
-      p.stage_bytes = (block_n / 2) * 128;                      // this CTA's half of a W tile
+    if (p.cta2) p.num_tiles = pair_tiles;
+    if (p.wres) {
+      p.num_slabs = static_cast<int>((SLAB_WRES_BYTES - w_all) / p.slab_bytes);
+      p.stage_bytes = block_n * 128;
+      p.num_stages = 1;
+    } else {
+      // W ring: 4 stages (N = 256) .. 8 stages (N <= 64); the slabs take the rest
+      p.stage_bytes = (p.cta2 ? block_n / 2 : block_n) * 128;
+      int want = block_n > 128 ? 4 : block_n > 64 ? 6 : 8;
+      p.num_slabs = (SLAB_DATA_BYTES - want * p.stage_bytes) / p.slab_bytes;
+      if (p.num_slabs < 2) p.num_slabs = 2;
+      if (p.num_slabs > SLAB_MAX_SLABS) p.num_slabs = SLAB_MAX_SLABS;
       p.num_stages = (SLAB_DATA_BYTES - p.num_slabs * p.slab_bytes) / p.stage_bytes;
       if (p.num_stages > MAX_STAGES) p.num_stages = MAX_STAGES;
-      p.num_tiles = pair_tiles;
     }
+    if (p.num_slabs > SLAB_MAX_SLABS) p.num_slabs = SLAB_MAX_SLABS;
   } else {
     p.stage_bytes = mt * A_BYTES + block_n * 128;
     p.num_stages = RING_BYTES / p.stage_bytes;
@@ -551,7 +574,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
                           static_cast<uint64_t>(a.B) * (a.H / 2)};
       uint64_t str[4] = {ct * 2, 2 * ct * 2, static_cast<uint64_t>(a.W) * ct * 2, 2 * static_cast<uint64_t>(a.W) * ct * 2};
       uint32_t box[5] = {BLOCK_K, 1, TILE_W, 1, TILE_H};
-      if (int rc = encode(tm, dt, 5, a.in[pl], dims, str, box, "A/down")) return rc;
+      if (int rc = encode(tm, dt, 5, a.in[pl], dims, str, box, "A/down", a_l2_promotion())) return rc;
     } else {
       uint64_t dims[4] = {static_cast<uint64_t>(a.cin), static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H),
                           static_cast<uint64_t>(a.B)};
@@ -562,7 +585,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
         box[1] = static_cast<uint32_t>(p.slab_w);
         box[2] = static_cast<uint32_t>(SLAB_TILE_H * mt + 2);
       }
-      if (int rc = encode(tm, dt, 4, a.in[pl], dims, str, box, slab ? "A/slab" : "A")) return rc;
+      if (int rc = encode(tm, dt, 4, a.in[pl], dims, str, box, slab ? "A/slab" : "A", a_l2_promotion())) return rc;
     }
   }
   {
