@@ -258,6 +258,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
     const float* bias = p.bias;
     const float* slope = p.slope;
     const bool staged = !WRES && p.epi_staged;
+    const bool nchw_small = p.out_kind == B200DN_OUT_NCHW32 && cout <= 4 && block_n == 16;
+    const int res_bmod = p.res_bmod > 0 ? p.res_bmod : 1;
+    const int64_t hw = static_cast<int64_t>(H) * W;
     uint8_t* stg = smem_gen + SLAB_DATA_BYTES + we * 4096;
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
@@ -268,10 +271,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
       float* ss = epi_slope + acc * MAX_N;
       stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et);
 
+      // Output block (fp32 NCHW, cout <= 4): fetch the fp32 residual (the network input) BEFORE waiting for the
+      // accumulator.  ncu showed the direct path serialising one DRAM round trip per channel behind the TMEM read
+      // (long_sb on each FADD), 10x above the layer's HBM time.
+      float pre[MT][4];
+      if (nchw_small) {
+        const int rb = t.b % res_bmod;
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+          const int y = t.y0 + j * TH + th, x = t.x0 + tw;
+          const bool valid = (y < H) && (x < W);
+          const int64_t sp = static_cast<int64_t>(y) * W + x;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            pre[j][c] = (valid && c < cout && p.res_nchw != nullptr)
+                            ? __ldg(p.res_nchw + (static_cast<int64_t>(rb) * cout + c) * hw + sp) : 0.f;
+        }
+      }
+
       mbar_wait(bars + B_TFULL + acc * 8, acc_phase);
       tc_fence_after();
 
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < MT; ++j) {
         const int y = t.y0 + j * TH + th, x = t.x0 + tw;
         const bool valid = (y < H) && (x < W);
@@ -279,7 +300,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n);
         const uint32_t rel = j == MT - 1 ? bars + B_TEMPTY + acc * 8 : 0u;
-        if (staged) {
+        if (nchw_small) {
+          uint32_t r[16];
+          tmem_ld16(taddr, r);
+          tmem_ld_wait();
+          if (rel != 0) {
+            tc_fence_before();
+            mbar_arrive(rel);
+          }
+          if (valid) {
+            const int64_t sp = static_cast<int64_t>(y) * W + x;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c < cout) {
+                const float a = __uint_as_float(r[c]) + bs[c];
+                p.out_nchw[(static_cast<int64_t>(t.b) * cout + c) * hw + sp] = (a > 0.f ? a : a * ss[c]) + pre[j][c];
+              }
+            }
+          }
+        } else if (staged) {
           RowMap rm;
           rm.b = t.b, rm.y0 = t.y0 + j * TH, rm.x0 = t.x0, rm.tw_shift = 3, rm.H = H, rm.W = W, rm.up = 0, rm.ky = 0, rm.kx = 0;
           epilogue_subtile_staged(ea, taddr, block_n, bs, ss, rm, we * 32, lane, t.n0, rel, stg);
