@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
     // ===================================================== W producer (both CTAs): HALF of each [N x 64] tap tile
     int ws = 0;
     uint32_t wph = 0;
-    const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128);   // both halves
+    const int w_taps = p.w_taps;
+    const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128 * w_taps);   // both halves of w_taps tap tiles
     const int pw0 = p.pair_w[0] * 9, pw1 = p.pair_w[1] * 9, pw2 = p.pair_w[2] * 9;
     for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters) {
       const TileCoord t = decode_pair_tile(tile, rank, p, TW, STH);
@@ -151,8 +152,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int wbase = pair == 0 ? pw0 : pair == 1 ? pw1 : pw2;
         for (int cb = 0; cb < n_cblk; ++cb) {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; tap += w_taps) {
             mbar_wait(bars + B_W_EMPTY + ws * 8, wph ^ 1u);
             if (elect_one()) {
               const uint32_t full = bars + B_W_FULL + ws * 8;
@@ -180,6 +181,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
       const int last_k16 = p.last_k16;
       const uint32_t pitch = static_cast<uint32_t>(p.slab_w * 128);   // bytes per slab pixel row = SBO
       const uint64_t row_step = static_cast<uint64_t>(pitch >> 4);    // descriptor address units (16 B)
+      const int w_taps = p.w_taps;
+      const uint64_t tap_step = static_cast<uint64_t>((half_n * 128) >> 4);   // this CTA's half of one tap tile
       WRing wr;
       wr.full0 = bars + B_W_FULL, wr.empty0 = bars + B_W_EMPTY;
       wr.full_end = wr.full0 + static_cast<uint32_t>(num_stages) * 8;
@@ -202,12 +205,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
           mbar_wait(bars + B_SLAB_FULL + s * 8, sph);
           const uint32_t slab = smem_base + static_cast<uint32_t>(s * slab_bytes) + static_cast<uint32_t>(j * TH) * pitch;
           uint64_t arow = make_sw128_desc(slab, pitch);
-          switch (nk) {   // one dispatch per 9 taps; inside, the k16 count is a compile-time constant
-            case 4: issue_slab_block_streamed<4, true>(d, arow, row_step, wr, idesc, accumulate); break;
-            case 3: issue_slab_block_streamed<3, true>(d, arow, row_step, wr, idesc, accumulate); break;
-            case 2: issue_slab_block_streamed<2, true>(d, arow, row_step, wr, idesc, accumulate); break;
-            default: issue_slab_block_streamed<1, true>(d, arow, row_step, wr, idesc, accumulate); break;
-          }
+          issue_slab_block_streamed_n<true>(nk, w_taps, d, arow, row_step, wr, tap_step, idesc, accumulate);
           if (elect_one()) {
             umma_commit_2cta(bars + B_SLAB_EMPTY + s * 8, 3);                       // both CTAs' slabs consumed
             if (kc == kc_iters - 1) umma_commit_2cta(bars + B_TFULL + acc * 8, 3);  // both accumulators complete

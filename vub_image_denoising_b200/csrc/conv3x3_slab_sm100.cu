@@ -145,15 +145,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
     // ===================================================== W-tile TMA producer: one [N x 64] tile per tap
     int ws = 0;
     uint32_t wph = 0;
-    const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128);
+    const int w_taps = p.w_taps;
+    const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128 * w_taps);   // one box = w_taps tap tiles
     const int pw0 = p.pair_w[0] * 9, pw1 = p.pair_w[1] * 9, pw2 = p.pair_w[2] * 9;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
       const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int wbase = pair == 0 ? pw0 : pair == 1 ? pw1 : pw2;
         for (int cb = 0; cb < n_cblk; ++cb) {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; tap += w_taps) {
             mbar_wait(bars + B_W_EMPTY + ws * 8, wph ^ 1u);
             if (elect_one()) {
               const uint32_t full = bars + B_W_FULL + ws * 8;
@@ -191,7 +192,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
     wr.desc0 = make_sw128_desc(wring, 1024);
     wr.step = static_cast<uint64_t>(stage_bytes >> 4);
     wr.full = wr.full0, wr.empty = wr.empty0, wr.phase = 0, wr.desc = wr.desc0;
-    const uint64_t bstep = static_cast<uint64_t>(w_tile_bytes >> 4);
+    const uint64_t bstep = static_cast<uint64_t>(w_tile_bytes >> 4);   // one [N x 64] tap tile
+    const int w_taps = p.w_taps;
     if (WRES) mbar_wait(bars + B_W_FULL, 0);   // resident weights have landed
     int s = 0;
     uint32_t sph = 0;
@@ -228,12 +230,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
           __syncwarp();
           accumulate = 1;
         } else {
-          switch (nk) {
-            case 4: issue_slab_block_streamed<4, false>(d, arow, row_step, wr, idesc, accumulate); break;
-            case 3: issue_slab_block_streamed<3, false>(d, arow, row_step, wr, idesc, accumulate); break;
-            case 2: issue_slab_block_streamed<2, false>(d, arow, row_step, wr, idesc, accumulate); break;
-            default: issue_slab_block_streamed<1, false>(d, arow, row_step, wr, idesc, accumulate); break;
-          }
+          issue_slab_block_streamed_n<false>(nk, w_taps, d, arow, row_step, wr, bstep, idesc, accumulate);
           if (elect_one()) {
             umma_commit(bars + B_SLAB_EMPTY + s * 8);                         // slab consumed by all 9 taps
             if (kc == kc_iters - 1) umma_commit(bars + B_TFULL + acc * 8);    // accumulator complete

@@ -33,6 +33,7 @@ struct __align__(64) KParams {
   int slab_w, slab_bytes, num_slabs, bo_mode;   // slab_bytes = ring slot stride (1 KB multiple)
   int slab_tx;                                  // bytes one slab TMA box delivers
   int wres, n_wplanes;   // weights resident in shared memory (small layers)
+  int w_taps;            // filter taps per streamed-W ring stage (1, or 3 = one filter row)
   int cta2, num_m_tiles; // CTA-pair kernel (cta_group::2): two spatial super tiles per W tile, one per CTA
   int epi_staged;        // smem-transposed epilogue with 128-byte-row global stores
   const float* bias;
@@ -371,19 +372,26 @@ struct WRing {
   }
 };
 
-// The 9 taps of one 64-channel block of a slab, weights streamed through the ring: per tap wait for the W tile,
-// issue NK UMMAs, commit the stage back to the W producer.  `arow` = descriptor of the slab row of tap (0, 0).
-template <int NK, bool CTA2>
+// The 9 taps of one 64-channel block of a slab, weights streamed through the ring.  WT = taps per ring stage:
+//   WT = 1: per tap wait for the W tile, issue NK UMMAs, commit the stage back to the W producer;
+//   WT = 3: one stage holds the three taps of a filter row (tiles `tap_step` apart), so the barrier wait, the commit
+//           and the ring bookkeeping are paid once per 3 taps — for N <= 64 (UMMAs of <= 32 clk) the issuer warp,
+//           not the tensor pipe, is what those instructions delay.
+// `arow` = descriptor of the slab row of tap (0, 0).
+template <int NK, bool CTA2, int WT>
 __device__ __forceinline__ void issue_slab_block_streamed(uint32_t d, uint64_t arow, uint64_t row_step, WRing& w,
-                                                          uint32_t idesc, uint32_t& accumulate) {
+                                                          uint64_t tap_step, uint32_t idesc, uint32_t& accumulate) {
 #pragma unroll 1
   for (int dy = 0; dy < 3; ++dy, arow += row_step) {
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
+    if (WT == 3) {
       mbar_wait(w.full, w.phase);
       tc_fence_after();
       if (elect_one()) {
-        issue_k16_steps<NK, CTA2>(d, arow + static_cast<uint64_t>(dx * 8), w.desc, idesc, accumulate);
+        uint64_t bdesc = w.desc;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx, bdesc += tap_step) {
+          issue_k16_steps<NK, CTA2>(d, arow + static_cast<uint64_t>(dx * 8), bdesc, idesc, dx == 0 ? accumulate : 1u);
+        }
         if (CTA2)
           umma_commit_2cta(w.empty, 3);
         else
@@ -392,6 +400,43 @@ __device__ __forceinline__ void issue_slab_block_streamed(uint32_t d, uint64_t a
       __syncwarp();
       accumulate = 1;
       w.advance();
+    } else {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        mbar_wait(w.full, w.phase);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_k16_steps<NK, CTA2>(d, arow + static_cast<uint64_t>(dx * 8), w.desc, idesc, accumulate);
+          if (CTA2)
+            umma_commit_2cta(w.empty, 3);
+          else
+            umma_commit(w.empty);
+        }
+        __syncwarp();
+        accumulate = 1;
+        w.advance();
+      }
+    }
+  }
+}
+template <bool CTA2>
+__device__ __forceinline__ void issue_slab_block_streamed_n(int nk, int wt, uint32_t d, uint64_t arow, uint64_t row_step,
+                                                            WRing& w, uint64_t tap_step, uint32_t idesc,
+                                                            uint32_t& accumulate) {
+  // one dispatch per 9 taps; inside, the k16 count and the stage shape are compile-time constants
+  if (wt == 3) {
+    switch (nk) {
+      case 4: issue_slab_block_streamed<4, CTA2, 3>(d, arow, row_step, w, tap_step, idesc, accumulate); break;
+      case 3: issue_slab_block_streamed<3, CTA2, 3>(d, arow, row_step, w, tap_step, idesc, accumulate); break;
+      case 2: issue_slab_block_streamed<2, CTA2, 3>(d, arow, row_step, w, tap_step, idesc, accumulate); break;
+      default: issue_slab_block_streamed<1, CTA2, 3>(d, arow, row_step, w, tap_step, idesc, accumulate); break;
+    }
+  } else {
+    switch (nk) {
+      case 4: issue_slab_block_streamed<4, CTA2, 1>(d, arow, row_step, w, tap_step, idesc, accumulate); break;
+      case 3: issue_slab_block_streamed<3, CTA2, 1>(d, arow, row_step, w, tap_step, idesc, accumulate); break;
+      case 2: issue_slab_block_streamed<2, CTA2, 1>(d, arow, row_step, w, tap_step, idesc, accumulate); break;
+      default: issue_slab_block_streamed<1, CTA2, 1>(d, arow, row_step, w, tap_step, idesc, accumulate); break;
     }
   }
 }

@@ -373,6 +373,14 @@ int cta2_mode() {
   }();
   return mode;
 }
+// B200DN_W_ROW_STAGES: 1 (default) = a streamed-W ring stage holds a filter row (3 taps) when N <= 64
+bool w_row_stages() {
+  static int on = [] {
+    const char* e = getenv("B200DN_W_ROW_STAGES");
+    return e ? atoi(e) : 1;
+  }();
+  return on != 0;
+}
 // B200DN_SLAB_PITCH: slab row pitch in pixels, 10 (default) .. 16 (the first version's layout)
 int slab_pitch() {
   static int w = [] {
@@ -499,14 +507,18 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     p.cta2 = (!p.wres && block_n >= 32 &&
               (impl == 3 || (a.impl == 0 && cta2_mode() == 1 && block_n >= 64 && pair_tiles >= sms / 2))) ? 1 : 0;
     if (p.cta2) p.num_tiles = pair_tiles;
+    p.w_taps = 1;
     if (p.wres) {
       p.num_slabs = static_cast<int>((SLAB_WRES_BYTES - w_all) / p.slab_bytes);
       p.stage_bytes = block_n * 128;
       p.num_stages = 1;
     } else {
-      // W ring: 4 stages (N = 256) .. 8 stages (N <= 64); the slabs take the rest
-      p.stage_bytes = (p.cta2 ? block_n / 2 : block_n) * 128;
-      int want = block_n > 128 ? 4 : block_n > 64 ? 6 : 8;
+      // W ring: one tap tile per stage, or a whole filter row (3 taps) per stage for N <= 64, where the per-stage
+      // barrier traffic of the issuer warp costs as much as the UMMAs it guards.  4 stages (N = 256) .. 8 stages;
+      // the slabs take the rest.
+      p.w_taps = (block_n <= 64 && w_row_stages()) ? 3 : 1;
+      p.stage_bytes = (p.cta2 ? block_n / 2 : block_n) * 128 * p.w_taps;
+      int want = p.w_taps == 3 ? (p.cta2 ? 5 : 4) : block_n > 128 ? 4 : block_n > 64 ? 6 : 8;
       p.num_slabs = (SLAB_DATA_BYTES - want * p.stage_bytes) / p.slab_bytes;
       if (p.num_slabs < 2) p.num_slabs = 2;
       if (p.num_slabs > SLAB_MAX_SLABS) p.num_slabs = SLAB_MAX_SLABS;
@@ -593,8 +605,9 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     uint64_t dims[3] = {static_cast<uint64_t>(cin_pad), static_cast<uint64_t>(cout_pad),
                         static_cast<uint64_t>(p.wgroups) * (two_w ? 2 : 1)};
     uint64_t str[2] = {static_cast<uint64_t>(cin_pad) * 2, static_cast<uint64_t>(cin_pad) * cout_pad * 2};
-    // resident mode: all 9 taps per box; CTA pairs: half of the N rows per CTA
-    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.cta2 ? block_n / 2 : block_n), p.wres ? 9u : 1u};
+    // resident mode: all 9 taps per box; streamed: w_taps taps per box; CTA pairs: half of the N rows per CTA
+    uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.cta2 ? block_n / 2 : block_n),
+                       p.wres ? 9u : static_cast<uint32_t>(slab ? p.w_taps : 1)};
     if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
   }
 
