@@ -260,7 +260,8 @@ def run_b200(args) -> None:
     summ = ROOT / "profiles" / "r01_bench_launches_summary.json"
     if summ.exists() and F == 128 and B == 64:
         traffic = json.loads(summ.read_text())["tensor_core_kernels"]["dram_bytes_per_launch"]
-    roofline = {"bound": "tensor", "kernel": "conv3x3_slab_kernel + igemm_kernel (68 tcgen05 launches per step)",
+    roofline = {"bound": "tensor", "kernel": "conv3x3_slab2_kernel (cta_group::2) + conv3x3_slab_kernel + igemm_kernel "
+                                             "(68 tcgen05 launches per step)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
                 "traffic_note": "dram__bytes_read+write per launch, mean over the 68 launches (ncu, profiles/r01_bench_launches.csv); "

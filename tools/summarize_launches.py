@@ -1,0 +1,84 @@
+"""Turn the ncu launch list of `bench.py` into the per-round profile files bench.py reads.
+
+    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+        -c 600 --csv --log-file gpurun_out/bench_launches.csv python bench.py --steps 2 --warmup 1 --skip-diffusion --skip-cpu
+    python tools/summarize_launches.py gpurun_out/bench_launches.csv profiles/r01_bench_launches
+
+Writes <out>.csv (one bench step, one line per launch, with a share-by-kernel header) and <out>_summary.json
+(`tensor_core_kernels.dram_bytes_per_launch` is what bench.py reports as roofline.traffic).  Per-launch times under
+ncu are cold-cache, serialised and at burst clocks: compare SHARES of the step, not absolute times.
+"""
+import csv
+import json
+import re
+import sys
+from collections import OrderedDict
+
+TENSOR = ("conv3x3_slab_kernel", "conv3x3_slab2_kernel", "igemm_kernel")
+
+
+def short(name: str) -> str:
+    name = re.sub(r"b200dn::|igemm::|<unnamed>::|\(anonymous namespace\)::|^void ", "", name)
+    name = re.sub(r"\(KParams\)", "", name)
+    name = name.replace("(int)", "").replace("(bool)", "")
+    return name.split("(const")[0].strip()[:110]
+
+
+def main() -> None:
+    src, out = sys.argv[1], sys.argv[2]
+    rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("==")) if len(r) >= 15]
+    hdr, rows = rows[0], rows[1:]
+    col = {h: i for i, h in enumerate(hdr)}
+    launches = OrderedDict()
+    for r in rows:
+        lid = int(r[col["ID"]])
+        d = launches.setdefault(lid, {"id": lid, "kernel": short(r[col["Kernel Name"]]),
+                                      "grid": r[col["Grid Size"]].replace(", ", "x").strip("()")})
+        v = float(r[col["Metric Value"]].replace(",", ""))
+        m = r[col["Metric Name"]]
+        if m == "gpu__time_duration.sum":
+            d["us"] = v / 1e3 if r[col["Metric Unit"]] in ("ns", "nsecond") else v
+        elif m == "dram__bytes_read.sum":
+            d["rd"] = v
+        elif m == "dram__bytes_write.sum":
+            d["wr"] = v
+    seq = list(launches.values())
+    # one bench step = from a gauss_noise launch up to (not including) the next one; take the last complete step
+    starts = [i for i, d in enumerate(seq) if "gauss_noise" in d["kernel"]]
+    if len(starts) < 2:
+        raise SystemExit("need at least two bench steps in the capture")
+    step = seq[starts[-2]:starts[-1]]
+    total_us = sum(d.get("us", 0.0) for d in step)
+    by = OrderedDict()
+    for d in step:
+        b = by.setdefault(d["kernel"], {"us": 0.0, "launches": 0, "rd": 0.0, "wr": 0.0})
+        b["us"] += d.get("us", 0.0)
+        b["launches"] += 1
+        b["rd"] += d.get("rd", 0.0)
+        b["wr"] += d.get("wr", 0.0)
+    tens = [d for d in step if any(t in d["kernel"] for t in TENSOR)]
+    t_us = sum(d["us"] for d in tens)
+    t_bytes = sum(d.get("rd", 0.0) + d.get("wr", 0.0) for d in tens)
+    cmd = "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python bench.py --steps 2 --warmup 1 --skip-diffusion --skip-cpu"
+    with open(out + ".csv", "w") as f:
+        f.write(f"# {cmd}\n# one bench step: RDUNet(128) bf16, B=64 x 256x256, noise + forward + PSNR/SSIM.  Cold-cache, serialised, "
+                "burst clocks: compare SHARES.\n# share by kernel (us, %, launches, DRAM read MB, DRAM write MB):\n")
+        for k, b in sorted(by.items(), key=lambda kv: -kv[1]["us"]):
+            f.write(f"#   {k:58s} {b['us']:10.1f} us {100 * b['us'] / total_us:5.1f}%  n={b['launches']:3d}  rd {b['rd'] / 1e6:10.1f}  wr {b['wr'] / 1e6:10.1f}\n")
+        f.write(f"#   total {total_us:.1f} us\nid,kernel,grid,us,dram_read_MB,dram_write_MB\n")
+        for d in step:
+            f.write(f"{d['id']},{d['kernel']},({d['grid']}),{d.get('us', 0):.1f},{d.get('rd', 0) / 1e6:.1f},{d.get('wr', 0) / 1e6:.1f}\n")
+    summary = {
+        "command": cmd + " (under ncu)", "step_total_us": total_us,
+        "tensor_core_kernels": {"launches": len(tens), "us": t_us, "share_of_step": t_us / total_us,
+                                "dram_bytes_per_step": t_bytes, "dram_bytes_per_launch": t_bytes / max(1, len(tens))},
+        "by_kernel": {k: {"us": b["us"], "share": b["us"] / total_us, "launches": b["launches"],
+                          "dram_read_MB": b["rd"] / 1e6, "dram_write_MB": b["wr"] / 1e6} for k, b in by.items()},
+    }
+    with open(out + "_summary.json", "w") as f:
+        json.dump(summary, f, indent=1)
+    print(json.dumps(summary["tensor_core_kernels"]))
+
+
+if __name__ == "__main__":
+    main()
