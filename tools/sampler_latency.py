@@ -26,4 +26,4 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 print(f"improved_sampling B={B} F={F} T={T} {dm.precision}: {ms:.3f} ms per call, {ms / B:.3f} ms per sample, "
-      f"{ms / (2 * T):.4f} ms per forward of {2 * B} images", flush=True)
+      f"{ms / T:.4f} ms per timestep (one forward of {2 * B} images + update)", flush=True)

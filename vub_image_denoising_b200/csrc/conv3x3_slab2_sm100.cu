@@ -232,14 +232,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
     const bool staged = p.epi_staged;
     uint8_t* stg = smem_gen + SLAB_DATA_BYTES + we * 4096;
     const uint32_t tempty_leader = mapa_shared(bars + B_TEMPTY, 0);
+    const bool one_n_tile = p.num_n_tiles == 1;
+    if (one_n_tile) stage_bias_slope(epi_bias, epi_slope, bias, slope, 0, block_n, cout, et);
     int local_tile = 0;
     for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters, ++local_tile) {
       const TileCoord t = decode_pair_tile(tile, rank, p, TW, STH);
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (local_tile >> 1) & 1;
-      float* bs = epi_bias + acc * MAX_N;
-      float* ss = epi_slope + acc * MAX_N;
-      stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et);
+      // bias / PReLU slopes of the tile's N range: staged once when the layer has a single N tile (per-tile global
+      // loads + a named barrier are a large share of a tile of the small-K layers), else per tile, double-buffered
+      float* bs = epi_bias + (one_n_tile ? 0 : acc * MAX_N);
+      float* ss = epi_slope + (one_n_tile ? 0 : acc * MAX_N);
+      if (!one_n_tile) stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et);
 
       mbar_wait(bars + B_TFULL + acc * 8, acc_phase);
       tc_fence_after();

@@ -41,8 +41,17 @@ constexpr uint32_t B_SLAB_FULL = 0, B_SLAB_EMPTY = 64, B_W_FULL = 128, B_W_EMPTY
 // per CTA and stays resident; the main loop then only streams slabs.  Used for the small layers (F = 32 levels 0/1),
 // which are latency-bound: per tile it removes 9 W-tile round trips and keeps the issue loop small enough for the
 // instruction cache (ncu: the unrolled 9-tap path showed mostly `no_inst` stalls there).
+// Epilogue warp groups: the resident-weight layers (N <= 48, K <= 9 * 128) do so little tensor work per output that
+// the epilogue's CUDA-core instruction stream is what paces a tile (measured: time proportional to pixels, independent
+// of K, of MT and of DRAM vs L2 residency; 4 epilogue warps run at ~0.27 IPC each).  With MT = 2 a second group of four
+// warps (hardware warps 8..11) drains sub-tile 1 while the first drains sub-tile 0.
 template <int MT, bool WRES>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __grid_constant__ KParams p) {
+constexpr int slab_epi_groups() { return (WRES && MT == 2) ? 2 : 1; }
+
+template <int MT, bool WRES>
+__global__ void __launch_bounds__(NUM_THREADS + EPI_THREADS * (slab_epi_groups<MT, WRES>() - 1), 1)
+conv3x3_slab_kernel(const __grid_constant__ KParams p) {
+  constexpr int EG = slab_epi_groups<MT, WRES>();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
@@ -74,7 +83,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bars + B_TFULL + a * 8, MT);
-      mbar_init(bars + B_TEMPTY + a * 8, EPI_THREADS);
+      mbar_init(bars + B_TEMPTY + a * 8, EPI_THREADS * EG);
     }
     mbar_fence_init();
   }
@@ -249,7 +258,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
     const int we = warp & 3;
     const int row = we * 32 + lane;
     const int th = row / TW, tw = row - th * TW;
-    const int et = threadIdx.x & (EPI_THREADS - 1);   // epilogue threads are hardware threads 0..127
+    const int eg = (EG == 2 && warp >= 8) ? 1 : 0;    // epilogue group (hardware warps 0..3 / 8..11)
+    const int et = (threadIdx.x & (EPI_THREADS - 1)) + eg * EPI_THREADS;
     const EpiArgs ea = make_epi_args(p);
     const int H = p.H, W = p.W, cout = p.cout;
     const float* bias = p.bias;
@@ -259,14 +269,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
     const int res_bmod = p.res_bmod > 0 ? p.res_bmod : 1;
     const int64_t hw = static_cast<int64_t>(H) * W;
     uint8_t* stg = smem_gen + SLAB_DATA_BYTES + we * 4096;
+    const bool one_n_tile = p.num_n_tiles == 1;
+    if (one_n_tile) stage_bias_slope(epi_bias, epi_slope, bias, slope, 0, block_n, cout, et, EPI_THREADS * EG);
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
       const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (local_tile >> 1) & 1;
-      float* bs = epi_bias + acc * MAX_N;
-      float* ss = epi_slope + acc * MAX_N;
-      stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et);
+      // bias / PReLU slopes of the tile's N range: staged once when the layer has a single N tile (per-tile global
+      // loads + a named barrier are a large share of a tile of the small-K layers), else per tile, double-buffered
+      float* bs = epi_bias + (one_n_tile ? 0 : acc * MAX_N);
+      float* ss = epi_slope + (one_n_tile ? 0 : acc * MAX_N);
+      if (!one_n_tile) stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et, EPI_THREADS * EG);
 
       // Output block (fp32 NCHW, cout <= 4): fetch the fp32 residual (the network input) BEFORE waiting for the
       // accumulator.  ncu showed the direct path serialising one DRAM round trip per channel behind the TMEM read
@@ -276,6 +290,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
         const int rb = t.b % res_bmod;
 #pragma unroll
         for (int j = 0; j < MT; ++j) {
+          if (EG == 2 && j != eg) continue;
           const int y = t.y0 + j * TH + th, x = t.x0 + tw;
           const bool valid = (y < H) && (x < W);
           const int64_t sp = static_cast<int64_t>(y) * W + x;
@@ -291,12 +306,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab_kernel(const __gr
 
 #pragma unroll
       for (int j = 0; j < MT; ++j) {
+        if (EG == 2 && j != eg) continue;   // two epilogue groups: one sub-tile each
         const int y = t.y0 + j * TH + th, x = t.x0 + tw;
         const bool valid = (y < H) && (x < W);
         const int64_t pix = (static_cast<int64_t>(t.b) * H + y) * W + x;
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n);
-        const uint32_t rel = j == MT - 1 ? bars + B_TEMPTY + acc * 8 : 0u;
+        const uint32_t rel = (EG == 2 || j == MT - 1) ? bars + B_TEMPTY + acc * 8 : 0u;
         if (nchw_small) {
           uint32_t r[16];
           tmem_ld16(taddr, r);
@@ -352,7 +368,8 @@ int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream) {
   });
   if (g_err != cudaSuccess) return cuda_fail(g_err, "cudaFuncSetAttribute(conv3x3_slab_kernel, smem)");
   KParams pc = p;
-  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[p.mt - 1][p.wres ? 1 : 0]), grid, NUM_THREADS,
+  const int threads = NUM_THREADS + ((p.mt == 2 && p.wres) ? EPI_THREADS : 0);   // second epilogue group
+  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[p.mt - 1][p.wres ? 1 : 0]), grid, threads,
                          SMEM_BYTES_SLAB, stream, &pc));
   return 0;
 }
