@@ -112,6 +112,44 @@ def test_conv3x3_tilings_agree(block_n, max_ctas, m_tiles, impl, built_lib):
     assert torch.equal(base_hi, out_hi)
 
 
+CTA_PAIR_CASES = [
+    # B, H, W, cin, cout, prec — shapes the default dispatch would NOT send to the pair kernel as well as ones it does
+    (3, 40, 24, 48, 48, _lib.PREC_BF16),        # 27 spatial tiles (odd): the last pair's second CTA computes a masked tile
+    (1, 16, 8, 64, 64, _lib.PREC_FP16),         # ONE spatial tile: a whole CTA of the only pair is masked
+    (2, 32, 48, 96, 128, _lib.PREC_BF16),       # partial last K block
+    (1, 16, 16, 64, 512, _lib.PREC_BF16),       # two N tiles of 256
+    (2, 24, 40, 160, 64, _lib.PREC_BF16X2),     # two (W, A) plane pairs, filter-row W stages
+    (1, 8, 8, 128, 256, _lib.PREC_BF16X3),      # three plane pairs
+    (5, 64, 64, 128, 64, _lib.PREC_BF16),       # enough tiles for several rounds per cluster, MT = 2
+]
+
+
+@pytest.mark.parametrize("max_ctas", [0, 2, 6])
+@pytest.mark.parametrize("case", CTA_PAIR_CASES, ids=[f"p{i}" for i in range(len(CTA_PAIR_CASES))])
+def test_conv3x3_cta_pair_bits_equal_single_cta(case, max_ctas, built_lib):
+    """The cta_group::2 kernel (each SM holds half of every W tile, M = 256 per UMMA) accumulates in the same order
+    as the one-CTA slab kernel: same bits, for any cluster count and for odd tile counts."""
+    B, H, W, cin, cout, prec = case
+    x = _rand(B, cin, H, W, seed=51)
+    w = _rand(cout, cin, 3, 3, seed=52, scale=(2.0 / (9 * cin)) ** 0.5)
+    bias = _rand(cout, seed=53, scale=0.1)
+    slope = torch.rand(cout, device=DEV) * 0.5
+    x_hi, x_lo = to_planes(x, prec)
+    wp = torch.ops.b200dn.pack_weight(w, prec, False)
+    res = _rand(B, cout, H, W, seed=54)
+    r_hi, r_lo = to_planes(res, prec)
+    outs = []
+    for impl, ctas in ((2, 0), (3, max_ctas)):
+        o_hi, o_lo = _mk_out(B, H, W, cout, prec)
+        torch.ops.b200dn.conv_igemm(x_hi, x_lo, wp, bias, slope, _lib.MODE_CONV3X3, prec, cin, cout, o_hi, o_lo, 0,
+                                    r_hi, r_lo, 0, ctas, 0, impl)
+        outs.append((o_hi, o_lo))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0])
+    if outs[0][1] is not None:
+        assert torch.equal(outs[0][1], outs[1][1])
+
+
 DOWN_CASES = [(1, 16, 32, 16, 32), (2, 24, 40, 64, 128), (1, 64, 64, 128, 256), (1, 8, 8, 32, 64)]
 
 

@@ -10,10 +10,35 @@ namespace b200dn {
 namespace {
 
 constexpr int PX = 32;     // pixels along W per block (one warp = 32 consecutive pixels: coalesced NCHW reads)
-constexpr int ROWS = 8;    // rows per pass (one warp each)
-constexpr int PASSES = 4;  // a block covers PX x (ROWS * PASSES) pixels, so the weights are staged once per 1024 px
+constexpr int ROWS = 8;    // warps per block; each thread owns TWO vertically adjacent pixels per pass
+constexpr int PASSES = 4;  // a block covers PX x (2 * ROWS * PASSES) pixels, so the weights are staged once per 2048 px
 
-// One thread = one pixel, all output channels in groups of 8 (weights broadcast from shared memory).
+template <bool kBf16>
+__device__ __forceinline__ void store_group(const float (&acc)[8], const float* b_s, const float* s_s, int g,
+                                            uint16_t* o0, uint16_t* o1) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = acc[2 * j] + b_s[g * 8 + 2 * j];
+    float c = acc[2 * j + 1] + b_s[g * 8 + 2 * j + 1];
+    a = a > 0.f ? a : a * s_s[g * 8 + 2 * j];
+    c = c > 0.f ? c : c * s_s[g * 8 + 2 * j + 1];
+    if (kBf16) {
+      hi[j] = pack_bf16x2(a, c);
+      lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), c - bf16_hi(hi[j]));
+    } else {
+      hi[j] = pack_f16x2(a, c);
+      lo[j] = pack_f16x2(a - f16_lo(hi[j]), c - f16_hi(hi[j]));
+    }
+  }
+  *reinterpret_cast<uint4*>(o0 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (o1 != nullptr) *reinterpret_cast<uint4*>(o1 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// One thread = two vertically adjacent pixels, all output channels in groups of 8.  The weights are broadcast from
+// shared memory (2 x LDS.128 per k and group); sharing them between two pixels halves the shared-memory reads per FMA
+// (the one-pixel version issued one LDS.128 per 4 FFMA and ran at a third of the FP32 rate), and the two pixels share
+// 8 of their 12 input rows x columns.
 template <int CIN>
 __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restrict__ x, int Bx,
                                                             const float* __restrict__ t, int64_t t_sb, int64_t t_sh,
@@ -45,58 +70,68 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
   if (xx >= W) return;
 
   for (int pass = 0; pass < PASSES; ++pass) {
-    const int y = (blockIdx.y * PASSES + pass) * ROWS + threadIdx.y;
+    const int y = ((blockIdx.y * PASSES + pass) * ROWS + threadIdx.y) * 2;   // rows y and y + 1
     if (y >= H) break;
-    float v[K];
+    const bool two = (y + 1) < H;
+    float v[CIN][4][3];   // input rows y-1 .. y+2, columns xx-1 .. xx+1
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
+    for (int r = 0; r < 4; ++r) {
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
-        const int yy = y + ky - 1, xc = xx + kx - 1;
+        const int yy = y + r - 1, xc = xx + kx - 1;
         const bool in = (yy >= 0) && (yy < H) && (xc >= 0) && (xc < W);
         const int64_t sp = static_cast<int64_t>(yy) * W + xc;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) v[ci * 9 + ky * 3 + kx] = in ? __ldg(xb + ci * hw + sp) : 0.f;
-        if (CIN == 4) v[27 + ky * 3 + kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
+        for (int ci = 0; ci < 3; ++ci) v[ci][r][kx] = in ? __ldg(xb + ci * hw + sp) : 0.f;
+        if (CIN == 4) v[3][r][kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
       }
     }
     const int64_t pix = (static_cast<int64_t>(b) * H + y) * W + xx;
     uint16_t* o0 = out0 + pix * out_ctot;
     uint16_t* o1 = out1 ? out1 + pix * out_ctot : nullptr;
+    const int64_t row = static_cast<int64_t>(W) * out_ctot;
     for (int g = 0; g * 8 < cout; ++g) {
-      float acc[8];
+      // packed fp32 FMAs (FFMA2: two IEEE fmas per instruction, same bits as fmaf) — the kernel is FP32-issue-bound
+      float2 p0[4], p1[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 4; ++j) p0[j] = p1[j] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8 + 4);
-        acc[0] = fmaf(v[k], w0.x, acc[0]);
-        acc[1] = fmaf(v[k], w0.y, acc[1]);
-        acc[2] = fmaf(v[k], w0.z, acc[2]);
-        acc[3] = fmaf(v[k], w0.w, acc[3]);
-        acc[4] = fmaf(v[k], w1.x, acc[4]);
-        acc[5] = fmaf(v[k], w1.y, acc[5]);
-        acc[6] = fmaf(v[k], w1.z, acc[6]);
-        acc[7] = fmaf(v[k], w1.w, acc[7]);
-      }
-      uint32_t hi[4], lo[4];
+      for (int ci = 0; ci < CIN; ++ci) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float a = acc[2 * j] + b_s[g * 8 + 2 * j];
-        float c = acc[2 * j + 1] + b_s[g * 8 + 2 * j + 1];
-        a = a > 0.f ? a : a * s_s[g * 8 + 2 * j];
-        c = c > 0.f ? c : c * s_s[g * 8 + 2 * j + 1];
-        if (is_bf16) {
-          hi[j] = pack_bf16x2(a, c);
-          lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), c - bf16_hi(hi[j]));
-        } else {
-          hi[j] = pack_f16x2(a, c);
-          lo[j] = pack_f16x2(a - f16_lo(hi[j]), c - f16_hi(hi[j]));
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int k = ci * 9 + ky * 3 + kx;
+            const float4 w0 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(w_s + k * cout + g * 8 + 4);
+            const float2 a = make_float2(v[ci][ky][kx], v[ci][ky][kx]);
+            const float2 c = make_float2(v[ci][ky + 1][kx], v[ci][ky + 1][kx]);
+            const float2 wa = make_float2(w0.x, w0.y), wb = make_float2(w0.z, w0.w);
+            const float2 wc = make_float2(w1.x, w1.y), wd = make_float2(w1.z, w1.w);
+            p0[0] = __ffma2_rn(a, wa, p0[0]);
+            p0[1] = __ffma2_rn(a, wb, p0[1]);
+            p0[2] = __ffma2_rn(a, wc, p0[2]);
+            p0[3] = __ffma2_rn(a, wd, p0[3]);
+            p1[0] = __ffma2_rn(c, wa, p1[0]);
+            p1[1] = __ffma2_rn(c, wb, p1[1]);
+            p1[2] = __ffma2_rn(c, wc, p1[2]);
+            p1[3] = __ffma2_rn(c, wd, p1[3]);
+          }
         }
       }
-      *reinterpret_cast<uint4*>(o0 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      if (o1 != nullptr) *reinterpret_cast<uint4*>(o1 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      float acc0[8], acc1[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc0[2 * j] = p0[j].x, acc0[2 * j + 1] = p0[j].y;
+        acc1[2 * j] = p1[j].x, acc1[2 * j + 1] = p1[j].y;
+      }
+      if (is_bf16) {
+        store_group<true>(acc0, b_s, s_s, g, o0, o1);
+        if (two) store_group<true>(acc1, b_s, s_s, g, o0 + row, o1 ? o1 + row : nullptr);
+      } else {
+        store_group<false>(acc0, b_s, s_s, g, o0, o1);
+        if (two) store_group<false>(acc1, b_s, s_s, g, o0 + row, o1 ? o1 + row : nullptr);
+      }
     }
   }
 }
@@ -115,12 +150,12 @@ extern "C" int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_
   B200DN_CHECK_ARG(prec >= 0 && prec <= 4, "conv_in: bad prec %d", prec);
   const bool two = (prec == B200DN_PREC_BF16X2 || prec == B200DN_PREC_BF16X3 || prec == B200DN_PREC_FP16X2);
   B200DN_CHECK_ARG(!two || out1, "conv_in: prec %d needs the lo output plane", prec);
-  B200DN_CHECK_ARG(B <= 65535 && H <= 65535 * ROWS * PASSES, "conv_in: B/H exceed the grid limit");
+  B200DN_CHECK_ARG(B <= 65535 && H <= 65535 * 2 * ROWS * PASSES, "conv_in: B/H exceed the grid limit");
   if (int rc = require_sm100()) return rc;
   const int cin = t ? 4 : 3;
   const size_t smem = (static_cast<size_t>(cin) * 9 + 2) * cout * sizeof(float);
   B200DN_CHECK_ARG(smem <= 160 * 1024, "conv_in: cout %d too large", cout);
-  dim3 block(PX, ROWS), grid(cdiv(W, PX), cdiv(H, ROWS * PASSES), B);
+  dim3 block(PX, ROWS), grid(cdiv(W, PX), cdiv(H, 2 * ROWS * PASSES), B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint16_t* o0 = static_cast<uint16_t*>(out0);
   uint16_t* o1 = two ? static_cast<uint16_t*>(out1) : nullptr;
