@@ -145,9 +145,11 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": "denoised_mpix_per_s", "value": value, "unit": "MPix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "RDUNet(base_filters=128) inference, 256x256 RGB patches, sigma in {10..50}, PSNR+SSIM",
-                   "global_batch": sample_batch, "patch": PATCH, "note": "reference CPU path (oracle port of the reference's "
-                   "PyTorch modules + numpy/scipy metrics) on the host cores; each step = 1 patch of the 64-patch batch"},
+        "config": {"workload": "RDUNet(base_filters=128) bf16 inference, batch 64 x 256x256 RGB per GPU, "
+                               "sigma cycling {10,20,30,40,50}, noise synthesis + PSNR/SSIM on device",
+                   "global_batch": sample_batch, "patch": PATCH, "note": "reference CPU path of that workload (oracle port of the "
+                   "reference's PyTorch modules in fp32 + numpy/scipy metrics) on the host cores; each step = 1 patch of the "
+                   "64-patch batch (bounded sample)"},
         "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": cores, "kind": "port",
                          "sample": f"{sample_batch} patch per step, mean of {args.steps} steps"},
         "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
