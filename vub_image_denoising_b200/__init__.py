@@ -6,8 +6,8 @@ CPU or PyTorch fallback.
 from ._lib import lib, lib_available, LIB_PATH  # noqa: F401
 from .rdunet import RDUNet, RDUNet_T, init_weights, ForwardPlan  # noqa: F401
 from .diffusion import DiffusionModel  # noqa: F401
-from . import metrics, noise, sharding, shim, ops  # noqa: F401
+from . import metrics, noise, sharding, shim, ops, sidd  # noqa: F401
 
 __all__ = ["RDUNet", "RDUNet_T", "DiffusionModel", "init_weights", "ForwardPlan", "metrics", "noise",
-           "sharding", "shim", "ops", "lib", "lib_available", "LIB_PATH"]
+           "sharding", "shim", "ops", "sidd", "lib", "lib_available", "LIB_PATH"]
 __version__ = "0.1.0"
