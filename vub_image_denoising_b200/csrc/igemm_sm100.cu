@@ -373,6 +373,15 @@ int cta2_mode() {
   }();
   return mode;
 }
+// B200DN_SPLIT_N: smallest N tile the under-filled-grid heuristic may choose (default 64; 0 or 256 = never split)
+int split_n_floor() {
+  static int v = [] {
+    const char* e = getenv("B200DN_SPLIT_N");
+    const int x = e ? atoi(e) : 64;
+    return x <= 0 ? 256 : x < 16 ? 16 : x;
+  }();
+  return v;
+}
 // B200DN_W_ROW_STAGES: 1 (default) = a streamed-W ring stage holds a filter row (3 taps) when N <= 64
 bool w_row_stages() {
   static int on = [] {
@@ -439,17 +448,26 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   p.cout = a.cout;
   const int cin_pad = round_up(a.cin, BLOCK_K);
   const int cout_pad = round_up(a.cout, 16);
+  int sms = device_sm_count();
+  if (sms <= 0) return B200DN_E_CUDA;
   int block_n = a.block_n;
   if (block_n == 0) {
     const int nt = cdiv(cout_pad, MAX_N);
     block_n = round_up(cdiv(cout_pad, nt), 16);
+    // Under-filled grid (batch 1-2, the deep levels): split N further, down to 64, until every SM has a tile (B200DN_SPLIT_N).  The
+    // reference's own scripts run batch_size = 1 (evaluate_model.py:318, evaluate_SIDD.py:116); there a level-3 layer
+    // has 8 pixel tiles, and 8 x (1024 / 256) tiles would leave 116 of 148 SMs idle.
+    const int th0 = a.mode == B200DN_MODE_CONV3X3 ? SLAB_TILE_H : TILE_H, tw0 = a.mode == B200DN_MODE_CONV3X3 ? SLAB_TILE_W : TILE_W;
+    const int64_t m_tiles1 = static_cast<int64_t>(p.B) * cdiv(p.W, tw0) * cdiv(p.H, th0);
+    const int groups = a.mode == B200DN_MODE_UP2X2 ? 4 : 1;
+    while (block_n >= split_n_floor() * 2 && (block_n / 2) % 16 == 0 && cout_pad % (block_n / 2) == 0 &&
+           m_tiles1 * cdiv(cout_pad, block_n) * groups < sms)
+      block_n /= 2;
   }
   B200DN_CHECK_ARG(block_n % 16 == 0 && block_n >= 16 && block_n <= MAX_N, "igemm: block_n %d invalid", block_n);
   p.block_n = block_n;
   p.n_tiles_per_group = cdiv(cout_pad, block_n);
   p.num_n_tiles = p.n_tiles_per_group * n_groups;
-  int sms = device_sm_count();
-  if (sms <= 0) return B200DN_E_CUDA;
   // accumulator tile: 16 x 8 pixels (tap kernel, sub-tiles side by side) or 8 x 16 (slab kernel, sub-tiles stacked)
   const int tw1 = slab ? SLAB_TILE_W : TILE_W, th1 = slab ? SLAB_TILE_H : TILE_H;
   // two A tiles per W tile (M = 256) when N is small enough for 4 accumulators in TMEM and there is enough
