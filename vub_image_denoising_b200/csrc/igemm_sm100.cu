@@ -365,7 +365,7 @@ bool wres_enabled() {
   }();
   return on != 0;
 }
-// B200DN_CTA2: 0 = never use the CTA-pair slab kernel, 1 = whenever legal and there is enough work (default)
+// B200DN_CTA2: 0 = never use the CTA-pair slab kernel, 1 = whenever legal (default), 2 = only when every SM pair gets a tile
 int cta2_mode() {
   static int mode = [] {
     const char* e = getenv("B200DN_CTA2");
@@ -520,10 +520,13 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     p.wres = (impl != 3 && p.num_n_tiles == 1 && block_n < 64 && w_all <= SLAB_WRES_BYTES - 2 * p.slab_bytes &&
               wres_enabled()) ? 1 : 0;
     // CTA pairs (cta_group::2, conv3x3_slab2_sm100.cu): each SM keeps half of every W tile.  Explicit impl 3, or by
-    // default for the streaming-weight layers (N >= 64) when every SM pair still gets at least one pair tile.
+    // default for the streaming-weight layers (N >= 64): when every SM pair gets at least one pair tile, and also
+    // when the grid is under-filled anyway (batch 1-2, deep levels) — there each CTA is paced by the latency of its
+    // own weight stream, which a pair halves, and 2 x pair tiles keep as many SMs busy as single-CTA tiles would.
     const int pair_tiles = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
+    const bool pairs_fit = pair_tiles >= sms / 2 || (cta2_mode() == 1 && p.num_tiles < sms && p.num_m_tiles >= 2);
     p.cta2 = (!p.wres && block_n >= 32 &&
-              (impl == 3 || (a.impl == 0 && cta2_mode() == 1 && block_n >= 64 && pair_tiles >= sms / 2))) ? 1 : 0;
+              (impl == 3 || (a.impl == 0 && cta2_mode() >= 1 && block_n >= 64 && pairs_fit))) ? 1 : 0;
     if (p.cta2) p.num_tiles = pair_tiles;
     p.w_taps = 1;
     if (p.wres) {
