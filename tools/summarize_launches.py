@@ -43,11 +43,14 @@ def main() -> None:
         elif m == "dram__bytes_write.sum":
             d["wr"] = v
     seq = list(launches.values())
-    # one bench step = from a gauss_noise launch up to (not including) the next one; take the last complete step
+    # one bench step = from a gauss_noise launch up to (not including) the next one.  Steps of the e2e leg may carry
+    # a second forward (CUDA-graph warm-up), so take the first complete step with the smallest launch count.
     starts = [i for i, d in enumerate(seq) if "gauss_noise" in d["kernel"]]
     if len(starts) < 2:
         raise SystemExit("need at least two bench steps in the capture")
-    step = seq[starts[-2]:starts[-1]]
+    segs = [seq[a:b] for a, b in zip(starts[:-1], starts[1:])]
+    fewest = min(len(g) for g in segs)
+    step = next(g for g in segs if len(g) == fewest)
     total_us = sum(d.get("us", 0.0) for d in step)
     by = OrderedDict()
     for d in step:
