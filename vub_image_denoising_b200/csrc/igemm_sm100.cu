@@ -255,14 +255,19 @@ igemm_kernel(const __grid_constant__ KParams p) {
     const bool staged = p.epi_staged;
     uint8_t* stg = smem_gen + RING_BYTES + (eg * 4 + we) * 4096;
     const int ncols = block_n / EG, col0 = eg * ncols;   // this group's share of the accumulator columns
+    const bool one_n_tile = n_tiles_per_group == 1;
+    if (one_n_tile) stage_bias_slope(epi_bias, epi_slope, bias, slope, 0, block_n, cout, et, EPI_THREADS * EG);
     int local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
       const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (local_tile >> 1) & 1;
-      float* bs = epi_bias + acc * MAX_N;
-      float* ss = epi_slope + acc * MAX_N;
-      stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et, EPI_THREADS * EG);
+      // bias / slopes depend on the tile's N offset only (not on the transposed conv's phase): staged once when every
+      // group has a single N tile — ncu showed the per-tile global loads (long_sb on the staging STS) on the epilogue's
+      // critical path of the short-K transposed convs
+      float* bs = epi_bias + (one_n_tile ? 0 : acc * MAX_N);
+      float* ss = epi_slope + (one_n_tile ? 0 : acc * MAX_N);
+      if (!one_n_tile) stage_bias_slope(bs, ss, bias, slope, t.n0, block_n, cout, et, EPI_THREADS * EG);
 
       mbar_wait(bars + 128 + acc * 8, acc_phase);
       tc_fence_after();
