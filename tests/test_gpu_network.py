@@ -167,6 +167,31 @@ def test_rdunet128_full_size_patch_vs_oracle(built_lib):
                 assert mx <= bound, f"{precision}: max err {mx:.3e}"
 
 
+def test_config2_full_batch_is_batch_consistent(built_lib):
+    """BASELINE config 2 at full size (RDUNet(128), 64 x 256x256, sigma cycling 10..50): a size-independent property.
+    Every op of the network is per-sample, so image i of the batch-64 forward (CTA-pair kernels, MT = 2 tiles, full
+    grids) must equal the batch-1 forward of that image (under-filled grids, split N tiles, different kernels) bit for
+    bit, and the on-device PSNR/SSIM of the batch must equal the per-image values."""
+    from oracle import metrics_oracle as mo
+    torch.manual_seed(7)
+    net = b2.RDUNet(base_filters=128).to(DEV).eval()
+    rng = np.random.default_rng(21)
+    clean_u8 = rng.integers(0, 256, size=(64, 256, 256, 3), dtype=np.uint8)
+    sigma = torch.tensor([(10.0, 20.0, 30.0, 40.0, 50.0)[i % 5] for i in range(64)], device=DEV)
+    _, noisy, clean = b2.noise.add_gaussian_noise(torch.from_numpy(clean_u8).to(DEV), sigma, seed=3, return_u8=False)
+    with torch.no_grad():
+        out = net(noisy)
+        assert torch.isfinite(out).all()
+        for i in (0, 17, 63):
+            one = net(noisy[i:i + 1].contiguous())
+            assert torch.equal(one[0], out[i]), f"image {i}: batch-64 and batch-1 forwards differ"
+    psnr, ssim = b2.metrics.batch_metrics(clean, out, 1.0)
+    for i in (0, 63):
+        c, o = clean[i].cpu().numpy(), out[i].cpu().numpy()
+        assert float(psnr[i]) == pytest.approx(mo.calculate_psnr(c, o, 1.0), abs=1e-4)
+        assert float(ssim[i]) == pytest.approx(mo.structural_similarity(c, o, data_range=1.0, channel_axis=0), abs=1e-5)
+
+
 def test_tiled_image_equals_untiled(built_lib):
     """BASELINE config 5 in small: halo-200 tiling (receptive-field radius 193) reproduces the untiled forward
     bit for bit; the only zero padding is at true image borders."""
