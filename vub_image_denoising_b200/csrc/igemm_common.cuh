@@ -82,10 +82,10 @@ __device__ __forceinline__ float cvt_hi(uint32_t v) {
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   if (kBf16) return pack_bf16x2(a, b);
-  // fp16 storage saturates instead of overflowing to inf
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  return pack_f16x2(a, b);
+  // fp16 storage saturates instead of overflowing to inf: one F2FP.SATFINITE instead of four FMNMX + F2FP
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
 
 struct EpiArgs {
