@@ -7,7 +7,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parent))
 from gpu_probe import conv_case, bench_layer  # noqa: E402
 from vub_image_denoising_b200 import _lib  # noqa: E402
 
-print("B200DN_SLAB_BO =", os.environ.get("B200DN_SLAB_BO", "(default 1)"), flush=True)
+# (the descriptor base-offset experiment, profiles/r01_umma_base_offset_experiment.txt, used a B200DN_SLAB_BO switch that
+# has since been removed: base_offset stays 0)
 worst = 0.0
 print("B200DN_SLAB_WRES =", os.environ.get("B200DN_SLAB_WRES", "(default 1)"), flush=True)
 for (B, H, W, cin, cout, prec, mt) in [(1, 16, 8, 64, 16, 0, 1), (2, 32, 24, 32, 16, 1, 2), (1, 16, 16, 80, 32, 4, 1), (1, 32, 8, 96, 32, 3, 2), (1, 16, 16, 64, 64, 0, 1), (2, 24, 40, 80, 48, 0, 1),

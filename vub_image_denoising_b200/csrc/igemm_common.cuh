@@ -30,7 +30,7 @@ struct __align__(64) KParams {
   int fmt;  // 1 bf16, 0 fp16
   int num_stages, stage_bytes, tmem_cols;
   // slab kernel only
-  int slab_w, slab_bytes, num_slabs, bo_mode;   // slab_bytes = ring slot stride (1 KB multiple)
+  int slab_w, slab_bytes, num_slabs;            // slab_bytes = ring slot stride (1 KB multiple)
   int slab_tx;                                  // bytes one slab TMA box delivers
   int wres, n_wplanes;   // weights resident in shared memory (small layers)
   int w_taps;            // filter taps per streamed-W ring stage (1, or 3 = one filter row)

@@ -517,7 +517,6 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     p.slab_w = slab_pitch();
     p.slab_tx = p.slab_w * (SLAB_TILE_H * mt + 2) * 128;
     p.slab_bytes = round_up(p.slab_tx, 1024);
-    p.bo_mode = 0;
     p.n_wplanes = two_w ? 2 : 1;
     const int64_t w_all = static_cast<int64_t>(p.n_wplanes) * p.n_cblk * 9 * block_n * 128;
     // small layers: keep the whole packed weight set resident in shared memory (single N tile only; cout < 64: such
