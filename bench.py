@@ -160,8 +160,25 @@ def run_reference(args) -> None:
 
 
 # ------------------------------------------------------------------------------------ B200 arm
+def ensure_library() -> None:
+    """libb200dn.so normally travels with the repo snapshot (built by __graft_entry__.build()); on a fresh checkout the
+    first local rank compiles it with nvcc and the others wait for it.  There is no fallback if it cannot be built."""
+    from vub_image_denoising_b200 import _build, _lib
+    if _lib.lib_available():
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        _build.build_lib()
+        return
+    t0 = time.time()
+    while not (_lib.lib_available() and _build.STAMP.exists()):
+        if time.time() - t0 > 600:
+            raise SystemExit("libb200dn.so was not built by local rank 0 within 10 minutes")
+        time.sleep(1.0)
+
+
 def run_b200(args) -> None:
     import torch.distributed as dist
+    ensure_library()
     import vub_image_denoising_b200 as b2
     from vub_image_denoising_b200 import sharding
 
