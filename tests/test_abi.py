@@ -40,6 +40,22 @@ def test_abi_version_and_struct_size(built_lib):
     assert ctypes.sizeof(_lib.IgemmArgs) == size
 
 
+def test_igemm_args_field_offsets_match_the_header(built_lib):
+    """Every field of the ctypes mirror sits where the C compiler puts it in struct b200dn_igemm_args."""
+    c_names = ["mode", "prec", "B", "H", "W", "cin", "cout", "in", "in_ctot", "wpacked", "bias", "slope", "out_kind",
+               "out", "out_ctot", "out_coff", "res", "res_ctot", "out_nchw", "res_nchw", "res_bmod", "block_n",
+               "max_ctas", "m_tiles", "impl"]
+    body = "".join(f'printf("%zu ", offsetof(b200dn_igemm_args, {n}));' for n in c_names)
+    src = f'#include "b200dn.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){{{body}return 0;}}'
+    exe = ROOT / "vub_image_denoising_b200" / "build" / "offsets_args"
+    exe.parent.mkdir(exist_ok=True)
+    subprocess.run(["gcc", "-x", "c", "-", "-I", str(ROOT / "include"), "-o", str(exe)], input=src, text=True, check=True)
+    offs = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    py_names = [n for n, _ in _lib.IgemmArgs._fields_]
+    assert [n.rstrip("_") for n in py_names] == c_names          # `in` is spelled `in_` in Python
+    assert [getattr(_lib.IgemmArgs, n).offset for n in py_names] == offs
+
+
 def test_packed_weight_bytes(built_lib):
     f = built_lib.b200dn_packed_weight_bytes
     assert f(16, 16, 9, _lib.PREC_BF16) == 9 * 16 * 64 * 2          # cin padded to 64
