@@ -192,6 +192,53 @@ def test_config2_full_batch_is_batch_consistent(built_lib):
         assert float(ssim[i]) == pytest.approx(mo.structural_similarity(c, o, data_range=1.0, channel_axis=0), abs=1e-5)
 
 
+def test_forward_graph_replay_and_user_capture(built_lib):
+    """The nn.Module forward replays its own CUDA graph from the second call on; a caller that captures the forward
+    into a graph of its own gets the eager launch list inside that capture.  All three give the same bits, for changing
+    inputs, and for RDUNet_T with scalar and per-sample timesteps."""
+    torch.manual_seed(3)
+    net = b2.RDUNet(base_filters=16).to(DEV).eval()
+    xs = [torch.rand(2, 3, 32, 48, device=DEV) * 2 - 1 for _ in range(3)]
+    with torch.no_grad():
+        first = net(xs[0])                      # call 1: eager
+        again = net(xs[0])                      # call 2: captures + replays
+        assert torch.equal(first, again)
+        outs = [net(x) for x in xs]             # replays with new inputs
+        plan = net.plan(2, 32, 48)
+        assert plan._graph is not None
+        ref = [torch.empty_like(x) for x in xs]
+        for x, r in zip(xs, ref):
+            plan.run(x, r)                      # eager launch list
+        torch.cuda.synchronize()
+        for o, r in zip(outs, ref):
+            assert torch.equal(o, r)
+        assert outs[0].data_ptr() != outs[1].data_ptr()      # fresh tensors, not views of the static buffer
+        # user-side capture
+        static_x = xs[1].clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            net(static_x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = net(static_x)
+        static_x.copy_(xs[2])
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y, ref[2])
+        # RDUNet_T: scalar and per-sample timesteps through the graph path
+        nt = b2.RDUNet_T(base_filters=16).to(DEV).eval()
+        t1 = torch.tensor([0.35], device=DEV).view(1, 1, 1, 1)
+        tb = torch.tensor([0.2, 0.9], device=DEV).view(2, 1, 1, 1)
+        a1, a2 = nt(xs[0], t1), nt(xs[0], t1)
+        b1_ = nt(xs[0], tb)
+        assert torch.equal(a1, a2)
+        one0 = nt(xs[0][:1].contiguous(), tb[:1])
+        one1 = nt(xs[0][1:].contiguous(), tb[1:])
+        assert torch.equal(b1_[0], one0[0]) and torch.equal(b1_[1], one1[0])
+
+
 def test_tiled_image_equals_untiled(built_lib):
     """BASELINE config 5 in small: halo-200 tiling (receptive-field radius 193) reproduces the untiled forward
     bit for bit; the only zero padding is at true image borders."""
