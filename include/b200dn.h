@@ -120,6 +120,28 @@ typedef struct b200dn_igemm_args {
 
 int b200dn_igemm(const b200dn_igemm_args* args, void* stream);
 
+/* The launch configuration b200dn_igemm would choose for `args` on a device with `sm_count` SMs, without touching the
+ * GPU (pointers are only checked for NULL).  Host-side tests sweep layer shapes through it to check that every choice
+ * fits the kernels' shared-memory / TMEM budgets; tools print it next to measured times. */
+typedef struct b200dn_igemm_plan_info {
+  int32_t kernel;          /* 0 per-tap kernel, 1 slab kernel (one CTA per tile), 2 slab kernel on CTA pairs          */
+  int32_t mt;              /* 128-pixel sub-tiles per CTA tile                                                        */
+  int32_t block_n;         /* UMMA N                                                                                  */
+  int32_t num_n_tiles;     /* N tiles (x4 phases for UP2X2)                                                           */
+  int32_t num_tiles;       /* tiles (pair tiles for kernel 2)                                                         */
+  int32_t grid;            /* CTAs launched                                                                           */
+  int32_t wres;            /* weights resident in shared memory                                                       */
+  int32_t num_slabs, slab_bytes;     /* slab ring (kernels 1, 2)                                                      */
+  int32_t num_stages, stage_bytes;   /* W ring (kernels 1, 2) or A+W ring (kernel 0)                                  */
+  int32_t w_taps;          /* filter taps per W ring stage                                                            */
+  int32_t tmem_cols;       /* TMEM columns allocated (power of two, <= 512)                                           */
+  int32_t epi_staged;      /* smem-transposed epilogue                                                                */
+  int32_t data_bytes_used; /* bytes of rings (+ resident weights) this launch places in shared memory                 */
+  int32_t data_bytes_budget; /* what the kernel's layout provides for them                                            */
+} b200dn_igemm_plan_info;
+
+int b200dn_igemm_plan(const b200dn_igemm_args* args, int sm_count, b200dn_igemm_plan_info* info);
+
 /* ---- input block conv_1 (Cin = 3 or 4), CUDA cores, fp32 math ---------------
  * x: fp32 NCHW [Bx,3,H,W]; image b of the output reads x[b % Bx].
  * t: optional timestep plane source; element (b,y,x) = t[b*t_sb + y*t_sh + x*t_sw]

@@ -24,7 +24,7 @@ OUT_NHWC16, OUT_NCHW32 = 0, 1
 EXPORTS = (
     "b200dn_last_error", "b200dn_abi_version", "b200dn_sm_count",
     "b200dn_pack_conv_weight", "b200dn_pack_convt_weight", "b200dn_packed_weight_bytes",
-    "b200dn_igemm", "b200dn_conv_in",
+    "b200dn_igemm", "b200dn_igemm_plan", "b200dn_conv_in",
     "b200dn_sampler_step", "b200dn_lerp",
     "b200dn_psnr_sse", "b200dn_ssim",
     "b200dn_gauss_noise_u8", "b200dn_philox_normal", "b200dn_u8_to_norm", "b200dn_norm_to_u8",
@@ -45,6 +45,13 @@ class IgemmArgs(C.Structure):
         ("out_nchw", C.c_void_p), ("res_nchw", C.c_void_p), ("res_bmod", C.c_int32),
         ("block_n", C.c_int32), ("max_ctas", C.c_int32), ("m_tiles", C.c_int32), ("impl", C.c_int32),
     ]
+
+
+class IgemmPlanInfo(C.Structure):
+    """struct b200dn_igemm_plan_info"""
+    _fields_ = [(n, C.c_int32) for n in (
+        "kernel", "mt", "block_n", "num_n_tiles", "num_tiles", "grid", "wres", "num_slabs", "slab_bytes", "num_stages",
+        "stage_bytes", "w_taps", "tmem_cols", "epi_staged", "data_bytes_used", "data_bytes_budget")]
 
 
 _lib = None
@@ -74,6 +81,7 @@ def lib() -> C.CDLL:
     L.b200dn_pack_conv_weight.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     L.b200dn_pack_convt_weight.argtypes = [vp, i32, i32, i32, vp, vp]
     L.b200dn_igemm.argtypes = [C.POINTER(IgemmArgs), vp]
+    L.b200dn_igemm_plan.argtypes = [C.POINTER(IgemmArgs), i32, C.POINTER(IgemmPlanInfo)]
     L.b200dn_conv_in.argtypes = [vp, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp]
     L.b200dn_sampler_step.argtypes = [vp, vp, vp, vp, f32, f32, f32, f32, vp, i64, vp]
     L.b200dn_lerp.argtypes = [vp, vp, f32, f32, vp, i64, vp]

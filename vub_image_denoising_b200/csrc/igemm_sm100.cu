@@ -416,7 +416,8 @@ CUtensorMapL2promotion a_l2_promotion() {
 
 }  // namespace
 
-int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
+int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream, b200dn_igemm_plan_info* info = nullptr,
+                 int sms_override = 0) {
   B200DN_CHECK_ARG(a.mode >= 0 && a.mode <= 3, "igemm: bad mode %d", a.mode);
   B200DN_CHECK_ARG(a.prec >= 0 && a.prec <= 4, "igemm: bad prec %d", a.prec);
   B200DN_CHECK_ARG(a.B > 0 && a.H > 0 && a.W > 0 && a.cin > 0 && a.cout > 0, "igemm: non-positive dims");
@@ -429,8 +430,12 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   B200DN_CHECK_ARG(!two_a || a.in[1], "igemm: prec %d needs the lo activation plane in[1]", a.prec);
   if (a.mode == B200DN_MODE_DOWN2X2)
     B200DN_CHECK_ARG(a.H % 2 == 0 && a.W % 2 == 0, "igemm: DOWN2X2 needs even H, W (got %d x %d)", a.H, a.W);
-  if (int rc = require_sm100()) return rc;
-  if (int rc = get_encoder()) return rc;
+  if (info == nullptr) {   // plan-only calls never touch the device
+    if (int rc = require_sm100()) return rc;
+    if (int rc = get_encoder()) return rc;
+  } else {
+    B200DN_CHECK_ARG(sms_override > 0, "igemm_plan: sm_count must be positive");
+  }
   const int impl = a.impl ? a.impl : default_conv3x3_impl();
   const bool slab = a.mode == B200DN_MODE_CONV3X3 && impl >= 2;
 
@@ -453,7 +458,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
   p.cout = a.cout;
   const int cin_pad = round_up(a.cin, BLOCK_K);
   const int cout_pad = round_up(a.cout, 16);
-  int sms = device_sm_count();
+  int sms = info ? sms_override : device_sm_count();
   if (sms <= 0) return B200DN_E_CUDA;
   int block_n = a.block_n;
   if (block_n == 0) {
@@ -599,6 +604,32 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     B200DN_CHECK_ARG(false, "igemm: bad out_kind %d", a.out_kind);
   }
 
+  int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
+  int clusters = 0;
+  if (slab && p.cta2) {
+    clusters = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
+    if (a.max_ctas > 0 && clusters > (a.max_ctas + 1) / 2) clusters = (a.max_ctas + 1) / 2;
+  }
+  if (info != nullptr) {
+    memset(info, 0, sizeof(*info));
+    info->kernel = slab ? (p.cta2 ? 2 : 1) : 0;
+    info->mt = mt, info->block_n = block_n, info->num_n_tiles = p.num_n_tiles, info->num_tiles = p.num_tiles;
+    info->grid = (slab && p.cta2) ? 2 * clusters : grid;
+    info->wres = p.wres, info->num_slabs = slab ? p.num_slabs : 0, info->slab_bytes = slab ? p.slab_bytes : 0;
+    info->num_stages = p.num_stages, info->stage_bytes = p.stage_bytes, info->w_taps = slab ? p.w_taps : 1;
+    info->tmem_cols = p.tmem_cols, info->epi_staged = p.epi_staged;
+    if (slab) {
+      const int w_bytes = p.wres ? p.n_wplanes * p.n_cblk * 9 * block_n * 128 : p.num_stages * p.stage_bytes;
+      info->data_bytes_used = p.num_slabs * p.slab_bytes + w_bytes;
+      info->data_bytes_budget = p.wres ? SLAB_WRES_BYTES : SLAB_DATA_BYTES;
+    } else {
+      info->data_bytes_used = p.num_stages * p.stage_bytes;
+      info->data_bytes_budget = RING_BYTES;
+    }
+    return 0;
+  }
+
   // ---- tensor maps
   const CUtensorMapDataType dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const uint64_t ct = static_cast<uint64_t>(a.in_ctot);
@@ -636,13 +667,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
     if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
   }
 
-  int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
-  if (slab && p.cta2) {
-    int clusters = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
-    if (a.max_ctas > 0 && clusters > (a.max_ctas + 1) / 2) clusters = (a.max_ctas + 1) / 2;
-    return launch_conv3x3_slab2(p, 2 * clusters, stream);
-  }
+  if (slab && p.cta2) return launch_conv3x3_slab2(p, 2 * clusters, stream);
   if (slab) return launch_conv3x3_slab(p, grid, stream);
 
   using KernelFn = void (*)(KParams);
@@ -662,6 +687,14 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream) {
 }
 
 }  // namespace b200dn
+
+extern "C" int b200dn_igemm_plan(const b200dn_igemm_args* args, int sm_count, b200dn_igemm_plan_info* info) {
+  if (!args || !info) {
+    b200dn::set_error("igemm_plan: null args / info");
+    return B200DN_E_ARG;
+  }
+  return b200dn::igemm_launch(*args, nullptr, info, sm_count);
+}
 
 extern "C" int b200dn_igemm(const b200dn_igemm_args* args, void* stream) {
   if (!args) {
