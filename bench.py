@@ -297,10 +297,9 @@ def run_b200(args) -> None:
     e2e_value = world * B * MPIX_PER_PATCH / (e2e_ms_total / args.steps / 1e3)
 
     # roofline of the dominant kernel (igemm_kernel): algorithmic FLOPs of the 68 launches / their device time
-    from oracle import rdunet_oracle
-    flops_img = rdunet_oracle.conv_flops(F)                        # 2*MAC of all 69 convs (SURVEY.md §8 d)
-    flops_in_conv = 2 * 9 * 3 * F * PATCH * PATCH
-    igemm_flops = (flops_img - flops_in_conv) * B
+    # 2*MAC of the 68 tensor-core convolutions of one step (SURVEY.md §8 d: F = 128 -> 1537.43 - 0.45 GFLOP per image),
+    # summed from the launch plan itself
+    igemm_flops = sum(info["flops"] for info in plan.layer_info)
     achieved = igemm_flops / (igemm_last_ms / 1e3) / 1e12
     # DRAM traffic of the same 68 launches from the committed ncu pass over this command (profiles/), per launch
     traffic = None

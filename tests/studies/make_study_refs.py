@@ -1,11 +1,11 @@
 """CPU (no GPU needed): fp32 oracle outputs of the 20-step sampler / RDUNet forward for several seeds, stored under
-tools/_study_refs/ (git-ignored, travels with the gpurun snapshot) so the GPU box only has to run the CUDA side."""
+tests/studies/_study_refs/ (git-ignored, travels with the gpurun snapshot) so the GPU box only has to run the CUDA side."""
 import sys
 from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 import vub_image_denoising_b200 as b2  # noqa: E402
 from oracle import rdunet_oracle as orc  # noqa: E402
 

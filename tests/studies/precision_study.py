@@ -1,11 +1,11 @@
-"""GPU: compare every 16-bit precision mode against the stored fp32 oracle outputs (tools/make_study_refs.py)."""
+"""GPU: compare every 16-bit precision mode against the stored fp32 oracle outputs (tests/studies/make_study_refs.py)."""
 import sys
 import time
 from pathlib import Path
 
 import torch
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 import vub_image_denoising_b200 as b2  # noqa: E402
 
 REFS = Path(__file__).resolve().parent / "_study_refs"

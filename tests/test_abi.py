@@ -98,6 +98,16 @@ def test_product_does_not_import_oracle():
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{py} imports the oracle"
     for src in (pkg / "csrc").iterdir():
         assert "oracle/" not in src.read_text() or src.name == "philox_normal.h", f"{src} references oracle/"
+    # developer tools are product-side too; studies that need the oracle live under tests/studies/
+    for py in (ROOT / "tools").glob("*.py"):
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", py.read_text(), flags=re.M), f"{py} imports the oracle"
+    # bench.py: the oracle is imported in the CPU-baseline / reference-arm function only
+    bench = (ROOT / "bench.py").read_text()
+    imports = [m.start() for m in re.finditer(r"^\s*(from|import)\s+oracle\b", bench, flags=re.M)]
+    assert len(imports) == 1
+    fn_start = bench.index("def cpu_reference_pass")
+    fn_end = bench.index("\ndef ", fn_start + 1)
+    assert fn_start < imports[0] < fn_end, "bench.py imports the oracle outside cpu_reference_pass"
 
 
 def test_shim_aliases():
