@@ -17,6 +17,10 @@
  *                           nn.Conv2d(C,2C,2,stride=2)+PReLU         UNet/RDUNet_model.py:49-56
  *                           nn.ConvTranspose2d(C,C,2,stride=2)+PReLU UNet/RDUNet_model.py:62,66-68
  *                           OutputBlock.conv_2 + `+ inputs`          UNet/RDUNet_model.py:83-93,186
+ *   b200dn_igemm_prepare / _launch / _launch_list / _rebind_nchw / _release
+ *                           the same layers as b200dn_igemm, with the launch configuration and the encoded tensor
+ *                           maps kept in an opaque handle: the ~70 modules RDUNet.forward chains per call
+ *                           (UNet/RDUNet_model.py:157-186) become one C call over a prebuilt list
  *   b200dn_conv_in          InputBlock.conv_1 + actv_1, t-plane cat  UNet/RDUNet_model.py:71-81,
  *                                                                    diffusion_denoising/Unet/Unet_model.py:133-136
  *   b200dn_pack_conv_weight / b200dn_pack_convt_weight
@@ -43,7 +47,7 @@
 extern "C" {
 #endif
 
-#define B200DN_ABI_VERSION 1
+#define B200DN_ABI_VERSION 2
 
 /* error codes */
 #define B200DN_OK          0
@@ -116,9 +120,25 @@ typedef struct b200dn_igemm_args {
   int32_t max_ctas;        /* 0 = one per SM                                         */
   int32_t m_tiles;         /* 0 = auto; 1 or 2 A tiles (128 pixels each) per W tile  */
   int32_t impl;            /* CONV3X3 only: 0 = default, 1 = per-tap reload, 2 = haloed slab, 3 = haloed slab on CTA pairs */
+  /* optional device int: OR'ed with 1 when an fp16-stored output value saturated at +-65504 (or was NaN).
+     Ignored for bf16 storage (fp32 exponent range) and for OUT_NCHW32.  NULL = no watch.               */
+  int32_t* sat_flag;
 } b200dn_igemm_args;
 
 int b200dn_igemm(const b200dn_igemm_args* args, void* stream);
+
+/* Prepared launches.  b200dn_igemm validates, plans and encodes 2-3 CUtensorMaps on every call (~25 us of host time);
+ * b200dn_igemm_prepare does that once and keeps the result, b200dn_igemm_launch / _launch_list only enqueue the
+ * kernel(s) (one cudaLaunchKernelExC each).  A handle is bound to the pointers in `args` and to the device that was
+ * current when it was prepared; only the OUT_NCHW32 output / residual pointers can be re-bound (they are the
+ * caller's tensors at the module boundary and change from call to call).  Handles are not thread-safe objects:
+ * do not rebind a handle while another thread launches it. */
+typedef struct b200dn_igemm_prepared b200dn_igemm_prepared;
+int b200dn_igemm_prepare(const b200dn_igemm_args* args, b200dn_igemm_prepared** out);
+int b200dn_igemm_rebind_nchw(b200dn_igemm_prepared* prep, float* out_nchw, const float* res_nchw, int res_bmod);
+int b200dn_igemm_launch(const b200dn_igemm_prepared* prep, void* stream);
+int b200dn_igemm_launch_list(b200dn_igemm_prepared* const* preps, int n, void* stream);
+void b200dn_igemm_release(b200dn_igemm_prepared* prep);
 
 /* The launch configuration b200dn_igemm would choose for `args` on a device with `sm_count` SMs, without touching the
  * GPU (pointers are only checked for NULL).  Host-side tests sweep layer shapes through it to check that every choice
@@ -147,11 +167,12 @@ int b200dn_igemm_plan(const b200dn_igemm_args* args, int sm_count, b200dn_igemm_
  * t: optional timestep plane source; element (b,y,x) = t[b*t_sb + y*t_sh + x*t_sw]
  *    (strides in elements, 0 = broadcast).  NULL -> 3-channel network.
  * w: OIHW fp32 [cout, 3|4, 3, 3].  Output: NHWC 16-bit planes, channels [0,cout).
+ * sat_flag: optional fp16 saturation watch, as in b200dn_igemm_args.
  */
 int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_sb, int64_t t_sh, int64_t t_sw,
                    int B, int H, int W, int cout,
                    const float* w, const float* bias, const float* slope,
-                   int prec, void* out0, void* out1, int out_ctot, void* stream);
+                   int prec, void* out0, void* out1, int out_ctot, int32_t* sat_flag, void* stream);
 
 /* ---- sampler elementwise ---------------------------------------------------- */
 /* x_next = (x - ((1-a_t)*u1 + a_t*y)) + ((1-a_p)*u2 + a_p*y), fp32, reference op order.

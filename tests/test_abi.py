@@ -30,7 +30,7 @@ def test_header_symbols_are_exported(built_lib):
 
 
 def test_abi_version_and_struct_size(built_lib):
-    assert built_lib.b200dn_abi_version() == 1
+    assert built_lib.b200dn_abi_version() == _lib.ABI_VERSION == 2
     # the ctypes mirror must have the C struct's size: 7 ints + pad, pointers ... computed by the C compiler
     src = '#include "b200dn.h"\n#include <stdio.h>\nint main(){printf("%zu", sizeof(b200dn_igemm_args));return 0;}'
     exe = ROOT / "vub_image_denoising_b200" / "build" / "sizeof_args"
@@ -44,7 +44,7 @@ def test_igemm_args_field_offsets_match_the_header(built_lib):
     """Every field of the ctypes mirror sits where the C compiler puts it in struct b200dn_igemm_args."""
     c_names = ["mode", "prec", "B", "H", "W", "cin", "cout", "in", "in_ctot", "wpacked", "bias", "slope", "out_kind",
                "out", "out_ctot", "out_coff", "res", "res_ctot", "out_nchw", "res_nchw", "res_bmod", "block_n",
-               "max_ctas", "m_tiles", "impl"]
+               "max_ctas", "m_tiles", "impl", "sat_flag"]
     body = "".join(f'printf("%zu ", offsetof(b200dn_igemm_args, {n}));' for n in c_names)
     src = f'#include "b200dn.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){{{body}return 0;}}'
     exe = ROOT / "vub_image_denoising_b200" / "build" / "offsets_args"
@@ -75,6 +75,26 @@ def test_no_gpu_means_error_not_fallback(built_lib):
         _lib.check(rc, "sampler_step")
     rc = built_lib.b200dn_igemm(None, None)
     assert rc == -1
+    # prepared launches: argument errors before any device work, a failed prepare leaves no handle behind
+    h = ctypes.c_void_p(123)
+    assert built_lib.b200dn_igemm_prepare(ctypes.byref(a), ctypes.byref(h)) == -1 and h.value is None
+    assert built_lib.b200dn_igemm_prepare(None, ctypes.byref(h)) == -1
+    assert built_lib.b200dn_igemm_launch(None, None) == -1
+    assert built_lib.b200dn_igemm_launch_list(None, 0, None) == -1
+    assert built_lib.b200dn_igemm_rebind_nchw(None, None, None, 0) == -1
+    built_lib.b200dn_igemm_release(None)          # releasing a null handle is a no-op
+
+
+def test_stale_library_is_refused(built_lib, tmp_path, monkeypatch):
+    """lib() compares the digest recorded at build time with the sources: an edited csrc/ must not run silently
+    against the old binary (the .so is git-ignored and travels with the snapshot)."""
+    from vub_image_denoising_b200 import _build
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_build, "_digest", lambda: "0" * 64)
+    with pytest.raises(RuntimeError, match="stale"):
+        _lib.lib()
+    monkeypatch.setenv("B200DN_ALLOW_STALE", "1")
+    assert _lib.lib() is not None
 
 
 def test_modules_refuse_cpu_tensors():

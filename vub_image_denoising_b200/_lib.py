@@ -11,6 +11,8 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libb200dn.so"
 
+ABI_VERSION = 2
+
 # enums (mirror include/b200dn.h)
 PREC_BF16, PREC_FP16, PREC_BF16X2, PREC_BF16X3, PREC_FP16X2 = 0, 1, 2, 3, 4
 PREC_NAMES = {"bf16": PREC_BF16, "fp16": PREC_FP16, "bf16x2": PREC_BF16X2, "bf16x3": PREC_BF16X3,
@@ -24,7 +26,8 @@ OUT_NHWC16, OUT_NCHW32 = 0, 1
 EXPORTS = (
     "b200dn_last_error", "b200dn_abi_version", "b200dn_sm_count",
     "b200dn_pack_conv_weight", "b200dn_pack_convt_weight", "b200dn_packed_weight_bytes",
-    "b200dn_igemm", "b200dn_igemm_plan", "b200dn_conv_in",
+    "b200dn_igemm", "b200dn_igemm_plan", "b200dn_igemm_prepare", "b200dn_igemm_rebind_nchw", "b200dn_igemm_launch",
+    "b200dn_igemm_launch_list", "b200dn_igemm_release", "b200dn_conv_in",
     "b200dn_sampler_step", "b200dn_lerp",
     "b200dn_psnr_sse", "b200dn_ssim",
     "b200dn_gauss_noise_u8", "b200dn_philox_normal", "b200dn_u8_to_norm", "b200dn_norm_to_u8",
@@ -44,6 +47,7 @@ class IgemmArgs(C.Structure):
         ("res", C.c_void_p * 2), ("res_ctot", C.c_int32),
         ("out_nchw", C.c_void_p), ("res_nchw", C.c_void_p), ("res_bmod", C.c_int32),
         ("block_n", C.c_int32), ("max_ctas", C.c_int32), ("m_tiles", C.c_int32), ("impl", C.c_int32),
+        ("sat_flag", C.c_void_p),
     ]
 
 
@@ -61,6 +65,20 @@ def lib_available() -> bool:
     return LIB_PATH.exists()
 
 
+def _check_fresh() -> None:
+    """The .so is git-ignored and travels with the snapshot: refuse to run against a binary whose recorded source
+    digest (build/sources.sha256, written by _build.build_lib) no longer matches csrc/ + include/b200dn.h, so that GPU
+    parity results always reflect the sources at HEAD.  B200DN_ALLOW_STALE=1 skips the check."""
+    import os
+    if os.environ.get("B200DN_ALLOW_STALE") == "1":
+        return
+    from . import _build
+    if _build.STAMP.exists() and _build.STAMP.read_text().strip() != _build._digest():
+        raise RuntimeError(
+            f"{LIB_PATH} is stale: csrc/ or include/b200dn.h changed since it was built.  Rebuild it with "
+            "`python -m vub_image_denoising_b200._build` (or __graft_entry__.build()).")
+
+
 def lib() -> C.CDLL:
     """Load (once) and return the library.  Raises if it has not been built."""
     global _lib
@@ -70,6 +88,7 @@ def lib() -> C.CDLL:
         raise RuntimeError(
             f"{LIB_PATH} is missing: build it with `python -m vub_image_denoising_b200._build` "
             "(or __graft_entry__.build()).  There is no fallback path.")
+    _check_fresh()
     L = C.CDLL(str(LIB_PATH))
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
     L.b200dn_last_error.restype = C.c_char_p
@@ -82,7 +101,13 @@ def lib() -> C.CDLL:
     L.b200dn_pack_convt_weight.argtypes = [vp, i32, i32, i32, vp, vp]
     L.b200dn_igemm.argtypes = [C.POINTER(IgemmArgs), vp]
     L.b200dn_igemm_plan.argtypes = [C.POINTER(IgemmArgs), i32, C.POINTER(IgemmPlanInfo)]
-    L.b200dn_conv_in.argtypes = [vp, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp]
+    L.b200dn_igemm_prepare.argtypes = [C.POINTER(IgemmArgs), C.POINTER(vp)]
+    L.b200dn_igemm_rebind_nchw.argtypes = [vp, vp, vp, i32]
+    L.b200dn_igemm_launch.argtypes = [vp, vp]
+    L.b200dn_igemm_launch_list.argtypes = [C.POINTER(vp), i32, vp]
+    L.b200dn_igemm_release.argtypes = [vp]
+    L.b200dn_igemm_release.restype = None
+    L.b200dn_conv_in.argtypes = [vp, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp]
     L.b200dn_sampler_step.argtypes = [vp, vp, vp, vp, f32, f32, f32, f32, vp, i64, vp]
     L.b200dn_lerp.argtypes = [vp, vp, f32, f32, vp, i64, vp]
     L.b200dn_psnr_sse.argtypes = [vp, vp, i64, i64, vp, vp]
@@ -93,9 +118,9 @@ def lib() -> C.CDLL:
     L.b200dn_norm_to_u8.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("b200dn_last_error", "b200dn_packed_weight_bytes"):
+        if name not in ("b200dn_last_error", "b200dn_packed_weight_bytes", "b200dn_igemm_release"):
             fn.restype = i32
-    if L.b200dn_abi_version() != 1:
+    if L.b200dn_abi_version() != ABI_VERSION:
         raise RuntimeError("libb200dn.so ABI version mismatch; rebuild the library")
     _lib = L
     return L

@@ -40,6 +40,13 @@ int require_sm100();   // 0 if the current device is compute capability 10.x
 // (cluster > 1: thread-block cluster of that many CTAs along x)
 cudaError_t launch_pdl(const void* kernel, int grid, int threads, size_t smem, cudaStream_t stream, void* params,
                        int cluster = 1);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) function attribute: a process that drives
+// several GPUs must opt every kernel in on each of them.  `done` is a per-family table indexed by device ordinal.
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+  bool done[kMaxDevices];
+};
+int ensure_max_dyn_smem(SmemOptIn& st, const void* const* kernels, int n, int bytes, const char* what);
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

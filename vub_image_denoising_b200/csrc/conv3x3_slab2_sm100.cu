@@ -20,7 +20,6 @@
 // Tile schedule: pair tile = (two consecutive spatial super tiles, one N tile); clusters take pair tiles round-robin.
 #include "igemm_common.cuh"
 
-#include <mutex>
 
 namespace b200dn {
 namespace igemm {
@@ -235,6 +234,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
     const bool one_n_tile = p.num_n_tiles == 1;
     if (one_n_tile) stage_bias_slope(epi_bias, epi_slope, bias, slope, 0, block_n, cout, et);
     int local_tile = 0;
+    uint32_t satm = 0;
     for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters, ++local_tile) {
       const TileCoord t = decode_pair_tile(tile, rank, p, TW, STH);
       const int acc = local_tile & 1;
@@ -259,12 +259,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
         if (staged) {
           RowMap rm;
           rm.b = t.b, rm.y0 = t.y0 + j * TH, rm.x0 = t.x0, rm.tw_shift = 3, rm.H = H, rm.W = W, rm.up = 0, rm.ky = 0, rm.kx = 0;
-          epilogue_subtile_staged(ea, taddr, block_n, bs, ss, rm, we * 32, lane, t.n0, rel, stg, true);
+          epilogue_subtile_staged(ea, taddr, block_n, bs, ss, rm, we * 32, lane, t.n0, rel, stg, satm, true);
         } else {
-          epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, pix, pix, t.n0, rel, true);
+          epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, pix, pix, t.n0, rel, satm, true);
         }
       }
     }
+    sat_report(ea.sat_flag, satm);
   }
 
   // Neither CTA may leave (or free its TMEM) while the other can still read its shared memory through an MMA or
@@ -277,26 +278,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
   }
 }
 
-std::once_flag g_once;
-cudaError_t g_err = cudaSuccess;
+SmemOptIn g_smem_opt_in;
 
 }  // namespace
 
-int launch_conv3x3_slab2(const KParams& p, int grid, cudaStream_t stream) {
+int resolve_conv3x3_slab2(LaunchCfg* cfg, int grid) {
+  const KParams& p = cfg->p;
   B200DN_CHECK_ARG(p.cta2 && !p.wres, "conv3x3 slab2: not a CTA-pair configuration");
   B200DN_CHECK_ARG(p.num_stages >= 2, "conv3x3 slab2: W ring too small for block_n %d", p.block_n);
   B200DN_CHECK_ARG(p.num_slabs <= MAX_SLABS, "conv3x3 slab2: too many slabs");
   B200DN_CHECK_ARG(grid >= 2 && grid % 2 == 0, "conv3x3 slab2: grid %d must be a positive multiple of 2", grid);
-  using KernelFn = void (*)(KParams);
-  static const KernelFn kernels[2] = {conv3x3_slab2_kernel<1>, conv3x3_slab2_kernel<2>};
-  std::call_once(g_once, [] {
-    for (int m = 0; m < 2 && g_err == cudaSuccess; ++m)
-      g_err = cudaFuncSetAttribute(kernels[m], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB2);
-  });
-  if (g_err != cudaSuccess) return cuda_fail(g_err, "cudaFuncSetAttribute(conv3x3_slab2_kernel, smem)");
-  KParams pc = p;
-  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[p.mt - 1]), grid, NUM_THREADS, SMEM_BYTES_SLAB2, stream,
-                         &pc, 2));
+  static const void* const kernels[2] = {reinterpret_cast<const void*>(conv3x3_slab2_kernel<1>),
+                                         reinterpret_cast<const void*>(conv3x3_slab2_kernel<2>)};
+  if (int rc = ensure_max_dyn_smem(g_smem_opt_in, kernels, 2, SMEM_BYTES_SLAB2,
+                                   "cudaFuncSetAttribute(conv3x3_slab2_kernel, smem)"))
+    return rc;
+  cfg->kernel = kernels[p.mt - 1];
+  cfg->grid = grid;
+  cfg->threads = NUM_THREADS;
+  cfg->smem = SMEM_BYTES_SLAB2;
+  cfg->cluster = 2;
   return 0;
 }
 

@@ -19,7 +19,6 @@
 // 1 / 3 = MMA issuers of sub-tile 0 / 1 (MT = 2 stacks two 8x16-pixel tiles vertically), 4..7 = epilogue.
 #include "igemm_common.cuh"
 
-#include <mutex>
 
 namespace b200dn {
 namespace igemm {
@@ -272,6 +271,7 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
     const bool one_n_tile = p.num_n_tiles == 1;
     if (one_n_tile) stage_bias_slope(epi_bias, epi_slope, bias, slope, 0, block_n, cout, et, EPI_THREADS * EG);
     int local_tile = 0;
+    uint32_t satm = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
       const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
       const int acc = local_tile & 1;
@@ -334,12 +334,13 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
         } else if (staged) {
           RowMap rm;
           rm.b = t.b, rm.y0 = t.y0 + j * TH, rm.x0 = t.x0, rm.tw_shift = 3, rm.H = H, rm.W = W, rm.up = 0, rm.ky = 0, rm.kx = 0;
-          epilogue_subtile_staged(ea, taddr, block_n, bs, ss, rm, we * 32, lane, t.n0, rel, stg);
+          epilogue_subtile_staged(ea, taddr, block_n, bs, ss, rm, we * 32, lane, t.n0, rel, stg, satm);
         } else {
-          epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, pix, pix, t.n0, rel);
+          epilogue_subtile(ea, taddr, block_n, bs, ss, valid, t.b, y, x, pix, pix, t.n0, rel, satm);
         }
       }
     }
+    sat_report(ea.sat_flag, satm);
   }
 
   tc_fence_before();
@@ -350,27 +351,26 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
   }
 }
 
-std::once_flag g_once;
-cudaError_t g_err = cudaSuccess;
+SmemOptIn g_smem_opt_in;
 
 }  // namespace
 
-int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream) {
+int resolve_conv3x3_slab(LaunchCfg* cfg, int grid) {
+  const KParams& p = cfg->p;
   B200DN_CHECK_ARG(p.wres || p.num_stages >= 2, "conv3x3 slab: W ring too small for block_n %d", p.block_n);
   B200DN_CHECK_ARG(p.num_slabs <= MAX_SLABS, "conv3x3 slab: too many slabs");
-  using KernelFn = void (*)(KParams);
-  static const KernelFn kernels[2][2] = {{conv3x3_slab_kernel<1, false>, conv3x3_slab_kernel<1, true>},
-                                         {conv3x3_slab_kernel<2, false>, conv3x3_slab_kernel<2, true>}};
-  std::call_once(g_once, [] {
-    for (int m = 0; m < 2 && g_err == cudaSuccess; ++m)
-      for (int w = 0; w < 2 && g_err == cudaSuccess; ++w)
-        g_err = cudaFuncSetAttribute(kernels[m][w], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SLAB);
-  });
-  if (g_err != cudaSuccess) return cuda_fail(g_err, "cudaFuncSetAttribute(conv3x3_slab_kernel, smem)");
-  KParams pc = p;
-  const int threads = NUM_THREADS + ((p.mt == 2 && p.wres) ? EPI_THREADS : 0);   // second epilogue group
-  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[p.mt - 1][p.wres ? 1 : 0]), grid, threads,
-                         SMEM_BYTES_SLAB, stream, &pc));
+  static const void* const kernels[4] = {reinterpret_cast<const void*>(conv3x3_slab_kernel<1, false>),
+                                         reinterpret_cast<const void*>(conv3x3_slab_kernel<1, true>),
+                                         reinterpret_cast<const void*>(conv3x3_slab_kernel<2, false>),
+                                         reinterpret_cast<const void*>(conv3x3_slab_kernel<2, true>)};
+  if (int rc = ensure_max_dyn_smem(g_smem_opt_in, kernels, 4, SMEM_BYTES_SLAB,
+                                   "cudaFuncSetAttribute(conv3x3_slab_kernel, smem)"))
+    return rc;
+  cfg->kernel = kernels[(p.mt - 1) * 2 + (p.wres ? 1 : 0)];
+  cfg->grid = grid;
+  cfg->threads = NUM_THREADS + ((p.mt == 2 && p.wres) ? EPI_THREADS : 0);   // second epilogue group
+  cfg->smem = SMEM_BYTES_SLAB;
+  cfg->cluster = 1;
   return 0;
 }
 

@@ -13,9 +13,20 @@ constexpr int PX = 32;     // pixels along W per block (one warp = 32 consecutiv
 constexpr int ROWS = 8;    // warps per block; each thread owns TWO vertically adjacent pixels per pass
 constexpr int PASSES = 4;  // a block covers PX x (2 * ROWS * PASSES) pixels, so the weights are staged once per 2048 px
 
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {   // saturates at +-65504 like the igemm epilogue
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t sat_track(uint32_t m, uint32_t h) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 a;\n\tabs.f16x2 a, %2;\n\tmax.NaN.f16x2 %0, %1, a;\n\t}" : "=r"(r) : "r"(m), "r"(h));
+  return r;
+}
+
 template <bool kBf16>
 __device__ __forceinline__ void store_group(const float (&acc)[8], const float* b_s, const float* s_s, int g,
-                                            uint16_t* o0, uint16_t* o1) {
+                                            uint16_t* o0, uint16_t* o1, uint32_t& satm) {
   uint32_t hi[4], lo[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -27,8 +38,9 @@ __device__ __forceinline__ void store_group(const float (&acc)[8], const float* 
       hi[j] = pack_bf16x2(a, c);
       lo[j] = pack_bf16x2(a - bf16_lo(hi[j]), c - bf16_hi(hi[j]));
     } else {
-      hi[j] = pack_f16x2(a, c);
-      lo[j] = pack_f16x2(a - f16_lo(hi[j]), c - f16_hi(hi[j]));
+      hi[j] = pack_f16x2_sat(a, c);
+      lo[j] = pack_f16x2_sat(a - f16_lo(hi[j]), c - f16_hi(hi[j]));
+      satm = sat_track(satm, hi[j]);
     }
   }
   *reinterpret_cast<uint4*>(o0 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -46,7 +58,7 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
                                                             const float* __restrict__ w, const float* __restrict__ bias,
                                                             const float* __restrict__ slope, int prec,
                                                             uint16_t* __restrict__ out0, uint16_t* __restrict__ out1,
-                                                            int out_ctot) {
+                                                            int out_ctot, int* __restrict__ sat_flag) {
   extern __shared__ float w_s[];  // [CIN*9][cout], then bias[cout], slope[cout]
   constexpr int K = CIN * 9;
   float* b_s = w_s + K * cout;
@@ -68,6 +80,7 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
   const float* xb = x + static_cast<int64_t>(b % Bx) * 3 * hw;
   const bool is_bf16 = (prec != B200DN_PREC_FP16) && (prec != B200DN_PREC_FP16X2);
   if (xx >= W) return;
+  uint32_t satm = 0;
 
   for (int pass = 0; pass < PASSES; ++pass) {
     const int y = ((blockIdx.y * PASSES + pass) * ROWS + threadIdx.y) * 2;   // rows y and y + 1
@@ -126,14 +139,15 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
         acc1[2 * j] = p1[j].x, acc1[2 * j + 1] = p1[j].y;
       }
       if (is_bf16) {
-        store_group<true>(acc0, b_s, s_s, g, o0, o1);
-        if (two) store_group<true>(acc1, b_s, s_s, g, o0 + row, o1 ? o1 + row : nullptr);
+        store_group<true>(acc0, b_s, s_s, g, o0, o1, satm);
+        if (two) store_group<true>(acc1, b_s, s_s, g, o0 + row, o1 ? o1 + row : nullptr, satm);
       } else {
-        store_group<false>(acc0, b_s, s_s, g, o0, o1);
-        if (two) store_group<false>(acc1, b_s, s_s, g, o0 + row, o1 ? o1 + row : nullptr);
+        store_group<false>(acc0, b_s, s_s, g, o0, o1, satm);
+        if (two) store_group<false>(acc1, b_s, s_s, g, o0 + row, o1 ? o1 + row : nullptr, satm);
       }
     }
   }
+  if (sat_flag != nullptr && (((satm & 0x7fffu) >= 0x7bffu) || ((satm >> 16) >= 0x7bffu))) atomicOr(sat_flag, 1);
 }
 
 }  // namespace
@@ -141,7 +155,7 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
 
 extern "C" int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_sb, int64_t t_sh, int64_t t_sw, int B,
                               int H, int W, int cout, const float* w, const float* bias, const float* slope, int prec,
-                              void* out0, void* out1, int out_ctot, void* stream) {
+                              void* out0, void* out1, int out_ctot, int32_t* sat_flag, void* stream) {
   using namespace b200dn;
   B200DN_CHECK_ARG(x && w && bias && slope && out0, "conv_in: null pointer");
   B200DN_CHECK_ARG(B > 0 && Bx > 0 && H > 0 && W > 0, "conv_in: non-positive dims");
@@ -163,12 +177,12 @@ extern "C" int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_
     if (smem > 48 * 1024)
       B200DN_CUDA(cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv_in_kernel<4><<<grid, block, smem, s>>>(x, Bx, t, t_sb, t_sh, t_sw, H, W, cout, w, bias, slope, prec, o0, o1,
-                                                out_ctot);
+                                                out_ctot, sat_flag);
   } else {
     if (smem > 48 * 1024)
       B200DN_CUDA(cudaFuncSetAttribute(conv_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv_in_kernel<3><<<grid, block, smem, s>>>(x, Bx, nullptr, 0, 0, 0, H, W, cout, w, bias, slope, prec, o0, o1,
-                                                out_ctot);
+                                                out_ctot, sat_flag);
   }
   B200DN_CUDA(cudaGetLastError());
   return 0;

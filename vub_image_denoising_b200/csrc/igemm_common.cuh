@@ -48,6 +48,7 @@ struct __align__(64) KParams {
   float* out_nchw;
   const float* res_nchw;
   int res_bmod;
+  int* sat_flag;         // optional: OR'ed with 1 when an fp16-stored output saturated (|v| >= 65504) or was NaN
 };
 
 struct TileCoord {
@@ -88,6 +89,17 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return r;
 }
 
+// fp16 saturation watch: running per-half maximum of |v| over the packed fp16 pairs a thread stores (NaN propagates);
+// one atomicOr per thread at most, and only if something saturated.
+__device__ __forceinline__ uint32_t sat_track(uint32_t m, uint32_t h) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 a;\n\tabs.f16x2 a, %2;\n\tmax.NaN.f16x2 %0, %1, a;\n\t}" : "=r"(r) : "r"(m), "r"(h));
+  return r;
+}
+__device__ __forceinline__ void sat_report(int* flag, uint32_t m) {
+  if (flag != nullptr && (((m & 0x7fffu) >= 0x7bffu) || ((m >> 16) >= 0x7bffu))) atomicOr(flag, 1);
+}
+
 struct EpiArgs {
   void* out0;
   void* out1;
@@ -98,6 +110,7 @@ struct EpiArgs {
   float* out_nchw;
   const float* res_nchw;
   int res_bmod, H, W;
+  int* sat_flag;
 };
 
 __device__ __forceinline__ EpiArgs make_epi_args(const KParams& p) {
@@ -106,13 +119,14 @@ __device__ __forceinline__ EpiArgs make_epi_args(const KParams& p) {
   e.out_ctot = p.out_ctot, e.out_coff = p.out_coff, e.res_ctot = p.res_ctot, e.cout = p.cout;
   e.out_kind = p.out_kind, e.is_bf16 = p.fmt != 0;
   e.out_nchw = p.out_nchw, e.res_nchw = p.res_nchw, e.res_bmod = p.res_bmod, e.H = p.H, e.W = p.W;
+  e.sat_flag = p.fmt != 0 ? nullptr : p.sat_flag;   // bf16 storage has fp32's exponent range: nothing to watch
   return e;
 }
 
 // 16 accumulator columns of one pixel -> 16 channels of the NHWC slice.
 template <bool kBf16>
 __device__ __forceinline__ void epilogue_nhwc16(const EpiArgs& e, float (&v)[16], int64_t out_pix, int64_t res_pix,
-                                                int ch0) {
+                                                int ch0, uint32_t& satm) {
   if (ch0 >= e.cout) return;
   const bool half1 = (ch0 + 8) < e.cout;  // second 8-channel group inside cout
   if (e.res0 != nullptr) {
@@ -141,6 +155,10 @@ __device__ __forceinline__ void epilogue_nhwc16(const EpiArgs& e, float (&v)[16]
   uint32_t hi[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) hi[j] = pack2<kBf16>(v[2 * j], v[2 * j + 1]);
+  if (!kBf16 && e.sat_flag != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) satm = sat_track(satm, hi[j]);
+  }
   uint4* o0 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(e.out0) + out_pix * e.out_ctot + e.out_coff + ch0);
   o0[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   if (half1) o0[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
@@ -162,7 +180,7 @@ __device__ __forceinline__ void epilogue_nhwc16(const EpiArgs& e, float (&v)[16]
 // `release_bar` != 0: arrive on it right after the last TMEM read (hands the accumulator stage back to the MMA warps).
 __device__ __forceinline__ void epilogue_subtile(const EpiArgs& e, uint32_t taddr, int block_n, const float* bs,
                                                  const float* ss, bool valid, int b, int y, int x, int64_t out_pix,
-                                                 int64_t res_pix, int n0, uint32_t release_bar,
+                                                 int64_t res_pix, int n0, uint32_t release_bar, uint32_t& satm,
                                                  bool cluster_rel = false) {
   for (int c0 = 0; c0 < block_n; c0 += 16) {
     uint32_t r[16];
@@ -197,9 +215,9 @@ __device__ __forceinline__ void epilogue_subtile(const EpiArgs& e, uint32_t tadd
     }
     if (e.out_kind == B200DN_OUT_NHWC16) {
       if (e.is_bf16)
-        epilogue_nhwc16<true>(e, v, out_pix, res_pix, n0 + c0);
+        epilogue_nhwc16<true>(e, v, out_pix, res_pix, n0 + c0, satm);
       else
-        epilogue_nhwc16<false>(e, v, out_pix, res_pix, n0 + c0);
+        epilogue_nhwc16<false>(e, v, out_pix, res_pix, n0 + c0, satm);
     } else {
       // fp32 NCHW output block: prelu(conv) + inputs   (UNet/RDUNet_model.py:186)
       const int64_t hw = static_cast<int64_t>(e.H) * e.W;
@@ -241,7 +259,7 @@ __device__ __forceinline__ bool row_pixels(const RowMap& m, int row, int64_t& ou
 
 __device__ __forceinline__ void epilogue_subtile_staged(const EpiArgs& e, uint32_t taddr, int block_n, const float* bs,
                                                         const float* ss, const RowMap& m, int row0, int lane, int n0,
-                                                        uint32_t release_bar, uint8_t* stg,
+                                                        uint32_t release_bar, uint8_t* stg, uint32_t& satm,
                                                         bool cluster_rel = false) {
   const uint32_t my_row = static_cast<uint32_t>(lane);
   const int sub_row = lane >> 3, chunk = lane & 7;   // coalesced phases: 4 rows x 8 chunks per instruction
@@ -317,6 +335,10 @@ __device__ __forceinline__ void epilogue_subtile_staged(const EpiArgs& e, uint32
       uint32_t h[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) h[j] = e.is_bf16 ? pack2<true>(v[2 * j], v[2 * j + 1]) : pack2<false>(v[2 * j], v[2 * j + 1]);
+      if (e.sat_flag != nullptr) {   // only set for fp16 storage
+#pragma unroll
+        for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
+      }
       *s0 = make_uint4(h[0], h[1], h[2], h[3]);
       *s1 = make_uint4(h[4], h[5], h[6], h[7]);
     }
@@ -454,10 +476,18 @@ __device__ __forceinline__ void issue_slab_block_resident(uint32_t d, uint64_t a
   }
 }
 
-// slab-kernel launcher (conv3x3_slab_sm100.cu); p is fully populated by igemm_launch
-int launch_conv3x3_slab(const KParams& p, int grid, cudaStream_t stream);
+// A fully resolved launch: kernel variant, launch geometry and the parameter block (with its encoded tensor maps).
+// b200dn_igemm builds one per call; b200dn_igemm_prepare keeps it, so that later launches cost one cudaLaunchKernelExC.
+struct LaunchCfg {
+  KParams p;
+  const void* kernel;
+  int grid, threads, smem, cluster;
+};
+// slab-kernel resolver (conv3x3_slab_sm100.cu); cfg->p is fully populated by igemm_configure.  Picks the template
+// variant and opts it in to its dynamic shared memory on the current device.
+int resolve_conv3x3_slab(LaunchCfg* cfg, int grid);
 // CTA-pair variant (conv3x3_slab2_sm100.cu); grid = 2 x clusters
-int launch_conv3x3_slab2(const KParams& p, int grid, cudaStream_t stream);
+int resolve_conv3x3_slab2(LaunchCfg* cfg, int grid);
 // shared-memory budget of the slab kernel, used by the host to size the rings
 constexpr int SLAB_DATA_BYTES = 200 * 1024;   // slab + W rings when the staged epilogue is in use
 constexpr int EPI_STAGING_BYTES = 16 * 1024;  // 4 epilogue warps x [32 rows x 128 B]

@@ -24,6 +24,7 @@
 
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <new>
 #include <stdlib.h>
 #include <string.h>
 
@@ -258,6 +259,7 @@ igemm_kernel(const __grid_constant__ KParams p) {
     const bool one_n_tile = n_tiles_per_group == 1;
     if (one_n_tile) stage_bias_slope(epi_bias, epi_slope, bias, slope, 0, block_n, cout, et, EPI_THREADS * EG);
     int local_tile = 0;
+    uint32_t satm = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
       const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
       const int acc = local_tile & 1;
@@ -289,12 +291,13 @@ igemm_kernel(const __grid_constant__ KParams p) {
           RowMap rm;
           rm.b = t.b, rm.y0 = t.y0, rm.x0 = t.x0 + j * TILE_W, rm.tw_shift = 4, rm.H = H, rm.W = W;
           rm.up = up ? 1 : 0, rm.ky = t.grp >> 1, rm.kx = t.grp & 1;
-          epilogue_subtile_staged(ea, taddr, ncols, bs + col0, ss + col0, rm, we * 32, lane, t.n0 + col0, rel, stg);
+          epilogue_subtile_staged(ea, taddr, ncols, bs + col0, ss + col0, rm, we * 32, lane, t.n0 + col0, rel, stg, satm);
         } else {
-          epilogue_subtile(ea, taddr, ncols, bs + col0, ss + col0, valid, t.b, y, x, out_pix, res_pix, t.n0 + col0, rel);
+          epilogue_subtile(ea, taddr, ncols, bs + col0, ss + col0, valid, t.b, y, x, out_pix, res_pix, t.n0 + col0, rel, satm);
         }
       }
     }
+    sat_report(ea.sat_flag, satm);
   }
 
   tc_fence_before();
@@ -341,8 +344,7 @@ int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, 
   return 0;
 }
 
-std::once_flag g_attr_once;
-cudaError_t g_attr_err = cudaSuccess;
+SmemOptIn g_smem_opt_in;
 
 // default conv3x3 implementation: 1 = per-tap reload (this file), 2 = haloed slab (conv3x3_slab_sm100.cu);
 // B200DN_CONV3X3_IMPL=tap|slab overrides, b200dn_igemm_args.impl overrides both.
@@ -416,8 +418,10 @@ CUtensorMapL2promotion a_l2_promotion() {
 
 }  // namespace
 
-int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream, b200dn_igemm_plan_info* info = nullptr,
-                 int sms_override = 0) {
+// Validate `a`, choose the kernel family / tiling / ring sizes and — unless this is a plan-only query (`info` set) —
+// encode the tensor maps and resolve the kernel variant into `cfg`.
+int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_plan_info* info = nullptr,
+                    int sms_override = 0) {
   B200DN_CHECK_ARG(a.mode >= 0 && a.mode <= 3, "igemm: bad mode %d", a.mode);
   B200DN_CHECK_ARG(a.prec >= 0 && a.prec <= 4, "igemm: bad prec %d", a.prec);
   B200DN_CHECK_ARG(a.B > 0 && a.H > 0 && a.W > 0 && a.cin > 0 && a.cout > 0, "igemm: non-positive dims");
@@ -431,6 +435,7 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream, b200dn_igemm_p
   if (a.mode == B200DN_MODE_DOWN2X2)
     B200DN_CHECK_ARG(a.H % 2 == 0 && a.W % 2 == 0, "igemm: DOWN2X2 needs even H, W (got %d x %d)", a.H, a.W);
   if (info == nullptr) {   // plan-only calls never touch the device
+    B200DN_CHECK_ARG(cfg != nullptr, "igemm: internal: no launch configuration to fill");
     if (int rc = require_sm100()) return rc;
     if (int rc = get_encoder()) return rc;
   } else {
@@ -439,8 +444,10 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream, b200dn_igemm_p
   const int impl = a.impl ? a.impl : default_conv3x3_impl();
   const bool slab = a.mode == B200DN_MODE_CONV3X3 && impl >= 2;
 
-  KParams p;
+  KParams p_local;
+  KParams& p = cfg ? cfg->p : p_local;
   memset(&p, 0, sizeof(p));
+  p.sat_flag = a.sat_flag;
   p.taps = a.mode == B200DN_MODE_CONV3X3 ? 9 : a.mode == B200DN_MODE_DOWN2X2 ? 4 : 1;
   p.wgroups = a.mode == B200DN_MODE_CONV3X3 ? 9 : a.mode == B200DN_MODE_CONV1X1 ? 1 : 4;
   const int n_groups = a.mode == B200DN_MODE_UP2X2 ? 4 : 1;
@@ -667,33 +674,45 @@ int igemm_launch(const b200dn_igemm_args& a, cudaStream_t stream, b200dn_igemm_p
     if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
   }
 
-  if (slab && p.cta2) return launch_conv3x3_slab2(p, 2 * clusters, stream);
-  if (slab) return launch_conv3x3_slab(p, grid, stream);
+  if (slab && p.cta2) return resolve_conv3x3_slab2(cfg, 2 * clusters);
+  if (slab) return resolve_conv3x3_slab(cfg, grid);
 
-  using KernelFn = void (*)(KParams);
-  static const KernelFn kernels[3][2] = {{igemm_kernel<0, 1>, igemm_kernel<0, 2>},
-                                         {igemm_kernel<1, 1>, igemm_kernel<1, 2>},
-                                         {igemm_kernel<2, 1>, igemm_kernel<2, 2>}};
-  std::call_once(g_attr_once, [] {
-    for (int m = 0; m < 3 && g_attr_err == cudaSuccess; ++m)
-      for (int t = 0; t < 2 && g_attr_err == cudaSuccess; ++t)
-        g_attr_err = cudaFuncSetAttribute(kernels[m][t], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  });
-  if (g_attr_err != cudaSuccess) return cuda_fail(g_attr_err, "cudaFuncSetAttribute(igemm_kernel, smem)");
+  static const void* const kernels[6] = {
+      reinterpret_cast<const void*>(igemm_kernel<0, 1>), reinterpret_cast<const void*>(igemm_kernel<0, 2>),
+      reinterpret_cast<const void*>(igemm_kernel<1, 1>), reinterpret_cast<const void*>(igemm_kernel<1, 2>),
+      reinterpret_cast<const void*>(igemm_kernel<2, 1>), reinterpret_cast<const void*>(igemm_kernel<2, 2>)};
+  if (int rc = ensure_max_dyn_smem(g_smem_opt_in, kernels, 6, SMEM_BYTES, "cudaFuncSetAttribute(igemm_kernel, smem)"))
+    return rc;
   const int mode_idx = a.mode == B200DN_MODE_CONV3X3 ? 0 : a.mode == B200DN_MODE_DOWN2X2 ? 1 : 2;
-  const int threads = NUM_THREADS + ((mode_idx == 2 && mt == 1) ? EPI_THREADS : 0);
-  B200DN_CUDA(launch_pdl(reinterpret_cast<const void*>(kernels[mode_idx][mt - 1]), grid, threads, SMEM_BYTES, stream, &p));
+  cfg->kernel = kernels[mode_idx * 2 + (mt - 1)];
+  cfg->grid = grid;
+  cfg->threads = NUM_THREADS + ((mode_idx == 2 && mt == 1) ? EPI_THREADS : 0);
+  cfg->smem = SMEM_BYTES;
+  cfg->cluster = 1;
+  return 0;
+}
+
+int igemm_launch_cfg(const LaunchCfg& cfg, cudaStream_t stream) {
+  // the parameter block is copied by the launch itself; nothing is re-encoded here
+  B200DN_CUDA(launch_pdl(cfg.kernel, cfg.grid, cfg.threads, static_cast<size_t>(cfg.smem), stream,
+                         const_cast<KParams*>(&cfg.p), cfg.cluster));
   return 0;
 }
 
 }  // namespace b200dn
+
+// the opaque handle of include/b200dn.h
+struct b200dn_igemm_prepared {
+  b200dn::igemm::LaunchCfg cfg;
+  int out_kind;
+};
 
 extern "C" int b200dn_igemm_plan(const b200dn_igemm_args* args, int sm_count, b200dn_igemm_plan_info* info) {
   if (!args || !info) {
     b200dn::set_error("igemm_plan: null args / info");
     return B200DN_E_ARG;
   }
-  return b200dn::igemm_launch(*args, nullptr, info, sm_count);
+  return b200dn::igemm_configure(*args, nullptr, info, sm_count);
 }
 
 extern "C" int b200dn_igemm(const b200dn_igemm_args* args, void* stream) {
@@ -701,5 +720,63 @@ extern "C" int b200dn_igemm(const b200dn_igemm_args* args, void* stream) {
     b200dn::set_error("igemm: null args");
     return B200DN_E_ARG;
   }
-  return b200dn::igemm_launch(*args, static_cast<cudaStream_t>(stream));
+  b200dn::igemm::LaunchCfg cfg;
+  if (int rc = b200dn::igemm_configure(*args, &cfg)) return rc;
+  return b200dn::igemm_launch_cfg(cfg, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int b200dn_igemm_prepare(const b200dn_igemm_args* args, b200dn_igemm_prepared** out) {
+  if (!args || !out) {
+    b200dn::set_error("igemm_prepare: null args / out");
+    return B200DN_E_ARG;
+  }
+  *out = nullptr;
+  b200dn_igemm_prepared* h = new (std::nothrow) b200dn_igemm_prepared;
+  if (!h) {
+    b200dn::set_error("igemm_prepare: out of host memory");
+    return B200DN_E_ARG;
+  }
+  if (int rc = b200dn::igemm_configure(*args, &h->cfg)) {
+    delete h;
+    return rc;
+  }
+  h->out_kind = args->out_kind;
+  *out = h;
+  return 0;
+}
+
+extern "C" int b200dn_igemm_rebind_nchw(b200dn_igemm_prepared* prep, float* out_nchw, const float* res_nchw, int res_bmod) {
+  if (!prep || prep->out_kind != B200DN_OUT_NCHW32 || !out_nchw) {
+    b200dn::set_error("igemm_rebind_nchw: needs a prepared OUT_NCHW32 launch and a non-null output");
+    return B200DN_E_ARG;
+  }
+  prep->cfg.p.out_nchw = out_nchw;
+  prep->cfg.p.res_nchw = res_nchw;
+  if (res_bmod > 0) prep->cfg.p.res_bmod = res_bmod;
+  return 0;
+}
+
+extern "C" int b200dn_igemm_launch(const b200dn_igemm_prepared* prep, void* stream) {
+  if (!prep) {
+    b200dn::set_error("igemm_launch: null handle");
+    return B200DN_E_ARG;
+  }
+  return b200dn::igemm_launch_cfg(prep->cfg, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200dn_igemm_launch_list(b200dn_igemm_prepared* const* preps, int n, void* stream) {
+  if (!preps || n < 0) {
+    b200dn::set_error("igemm_launch_list: bad arguments");
+    return B200DN_E_ARG;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (!preps[i]) {
+      b200dn::set_error("igemm_launch_list: null handle at %d", i);
+      return B200DN_E_ARG;
+    }
+    if (int rc = b200dn::igemm_launch_cfg(preps[i]->cfg, static_cast<cudaStream_t>(stream))) return rc;
+  }
+  return 0;
+}
+
+extern "C" void b200dn_igemm_release(b200dn_igemm_prepared* prep) { delete prep; }

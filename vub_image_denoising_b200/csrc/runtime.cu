@@ -1,6 +1,7 @@
 // runtime.cu — error reporting and device queries of libb200dn.
 #include "common.cuh"
 
+#include <mutex>
 #include <string.h>
 #include <stdlib.h>
 
@@ -23,7 +24,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 namespace {
-constexpr int kMaxDev = 64;
+constexpr int kMaxDev = kMaxDevices;
 int g_sm_count[kMaxDev];
 int g_cc_major[kMaxDev];
 bool g_have[kMaxDev];
@@ -65,6 +66,26 @@ int require_sm100() {
               g_cc_major[dev]);
     return B200DN_E_CUDA;
   }
+  return 0;
+}
+
+int ensure_max_dyn_smem(SmemOptIn& st, const void* const* kernels, int n, int bytes, const char* what) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+  if (dev < 0 || dev >= kMaxDevices) {
+    set_error("device ordinal %d out of range", dev);
+    return B200DN_E_CUDA;
+  }
+  if (st.done[dev]) return 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (st.done[dev]) return 0;
+  for (int i = 0; i < n; ++i) {
+    e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+  }
+  st.done[dev] = true;
   return 0;
 }
 

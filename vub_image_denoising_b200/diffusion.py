@@ -16,13 +16,14 @@ B200 design of ``improved_sampling``:
 from __future__ import annotations
 
 import os
+import warnings
 from typing import Optional
 
 import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, ops
 from .rdunet import RDUNet_T, _RDUNetBase
 
 __all__ = ["DiffusionModel", "SAMPLER_PREC"]
@@ -35,6 +36,11 @@ __all__ = ["DiffusionModel", "SAMPLER_PREC"]
 #   fp16x2  100 %, max err 4e-4 .. 7.5e-4 (fp16 hi+lo activations, 2 MMAs)
 #   bf16x3  max err <= 5.4e-5 (fp32-validation build, 3 MMAs)
 SAMPLER_PREC = os.environ.get("B200DN_SAMPLER_PREC", "fp16")
+# fp16 storage has 5 exponent bits: activations beyond +-65504 saturate in the epilogue (cvt.rn.satfinite) instead of
+# becoming inf.  Random-init and the reference's trained checkpoints keep O(1) activations, but nothing guarantees it
+# for an arbitrary checkpoint, so every fp16 launch raises a device flag when it clamps a value and improved_sampling
+# re-runs the call in this (bf16-range) mode when the flag is set.
+SAT_FALLBACK_PREC = os.environ.get("B200DN_SAMPLER_FALLBACK_PREC", "bf16x2")
 
 
 def _f32(v: float) -> float:
@@ -67,7 +73,10 @@ class _SamplerState:
         self.t_all = torch.tensor(rows, dtype=torch.float32, device=dev).contiguous()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.result = self.y  # set by _enqueue
-        if use_graph and T > 0:
+        self.state_id = ops.register_plan(self)     # handle the torch.ops.b200dn.improved_sampling custom op takes
+        # a first call made while the caller is itself capturing a graph must not synchronise or start a nested
+        # capture: it runs the launch list eagerly inside the caller's capture
+        if use_graph and T > 0 and not torch.cuda.is_current_stream_capturing():
             # warm-up run on a side stream (lazy module loads, smem attribute), then capture
             s = torch.cuda.Stream(device=dev)
             s.wait_stream(torch.cuda.current_stream(dev))
@@ -96,11 +105,18 @@ class _SamplerState:
 
     def sample(self, noisy: torch.Tensor) -> torch.Tensor:
         self.y.copy_(noisy)
-        if self.graph is not None:
+        if self.plan.sat_flag is not None:
+            self.plan.sat_flag.zero_()
+        if self.graph is not None and not torch.cuda.is_current_stream_capturing():
             self.graph.replay()
         else:
             self._enqueue()
         return self.result.clone()
+
+    def saturated(self) -> bool:
+        """True if an fp16-stored activation was clamped at +-65504 (or was NaN) during the last ``sample``.
+        Reads one int from the device (synchronises the current stream)."""
+        return self.plan.sat_flag is not None and bool(int(self.plan.sat_flag.item()))
 
 
 class DiffusionModel(nn.Module):
@@ -110,6 +126,11 @@ class DiffusionModel(nn.Module):
         self.timesteps = timesteps
         self.precision = SAMPLER_PREC
         self.use_cuda_graph = os.environ.get("B200DN_GRAPH", "1") != "0"
+        # fp16 saturation guard: check the device flag after every fp16 sampling call (one 4-byte D2H read) and re-run
+        # at `saturation_fallback` precision if anything was clamped; `last_saturated` records what happened
+        self.check_saturation = os.environ.get("B200DN_SAT_CHECK", "1") != "0"
+        self.saturation_fallback = SAT_FALLBACK_PREC
+        self.last_saturated = False
         self._states: dict = {}
 
     # caches must not survive .to()/.cuda() or pickling
@@ -149,17 +170,32 @@ class DiffusionModel(nn.Module):
         if not isinstance(unet, RDUNet_T):
             return self._generic_sampling(noisy_image)
         y = unet._check_input(noisy_image)
+        st = self._state(y, self.precision)
+        out = torch.ops.b200dn.improved_sampling(y, st.state_id)
+        self.last_saturated = False
+        if (self.check_saturation and st.plan.sat_flag is not None and not torch.cuda.is_current_stream_capturing()
+                and st.saturated()):
+            self.last_saturated = True
+            warnings.warn(f"improved_sampling: {self.precision} activations saturated at +-65504; re-running this "
+                          f"call in {self.saturation_fallback} (set DiffusionModel.precision to avoid the retry)",
+                          RuntimeWarning, stacklevel=2)
+            st = self._state(y, self.saturation_fallback)
+            out = torch.ops.b200dn.improved_sampling(y, st.state_id)
+        return out
+
+    def _state(self, y: torch.Tensor, precision: str) -> "_SamplerState":
+        unet = self.unet
         B, _, H, W = y.shape
         T = int(self.timesteps)
-        key = (B, H, W, T, self.precision, self.use_cuda_graph)
+        key = (B, H, W, T, precision, self.use_cuda_graph)
         with torch.cuda.device(y.device):
             st = self._states.get(key)
             if st is None or st.signature != unet._param_signature():
                 if st is None and len(self._states) >= 2:
                     self._states.pop(next(iter(self._states)))
-                st = _SamplerState(self, B, H, W, T, self.precision, self.use_cuda_graph)
+                st = _SamplerState(self, B, H, W, T, precision, self.use_cuda_graph)
                 self._states[key] = st
-            return st.sample(y)
+        return st
 
     def _generic_sampling(self, noisy_image: torch.Tensor) -> torch.Tensor:
         """Any other ``unet(x, t)`` module: reference loop with the fused step kernel."""

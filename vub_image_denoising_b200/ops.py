@@ -1,12 +1,20 @@
-"""``torch.ops.b200dn.*`` — thin torch.library custom ops over the C ABI of libb200dn.so.
+"""``torch.ops.b200dn.*`` — the torch.library custom-op layer over the C ABI of libb200dn.so.
 
-Each op validates nothing beyond device/dtype and forwards raw pointers to the matching ``b200dn_*``
-entry point on the current CUDA stream.  The network modules use the same entry points through prebuilt
-argument blocks (rdunet.ForwardPlan); these ops are the functional, per-layer surface (used by the
-layer-level parity tests and available to callers that want a single fused layer).
+Two kinds of ops live here:
+
+* **network-level ops** — ``b200dn::rdunet_forward`` and ``b200dn::improved_sampling``.  These are the product call
+  path: ``RDUNet.forward`` / ``RDUNet_T.forward`` / ``DiffusionModel.improved_sampling`` dispatch through them, so the
+  whole fused forward (1 ingest launch + 68 prepared tcgen05 launches) or the whole sampling loop is ONE opaque node for
+  the dispatcher, with a fake (meta) implementation so that ``torch.compile``-d callers trace through it.  The op takes
+  the id of a prebuilt launch plan (packed weights, workspaces, encoded tensor maps) registered by the module.
+* **layer-level ops** — ``pack_weight``, ``conv_igemm``, ``conv_out_nchw``, ``conv_in``, ``sampler_step``: the
+  functional per-layer surface; each forwards raw pointers to the matching ``b200dn_*`` entry point on the current
+  CUDA stream (used by the layer-level parity tests and by callers that want a single fused layer).
 """
 from __future__ import annotations
 
+import itertools
+import weakref
 from typing import Optional
 
 import torch
@@ -14,7 +22,27 @@ import torch
 from . import _lib
 from ._lib import IgemmArgs
 
-__all__ = ["pack_weight", "conv_igemm", "conv_out_nchw", "conv_in", "sampler_step"]
+__all__ = ["pack_weight", "conv_igemm", "conv_out_nchw", "conv_in", "sampler_step", "rdunet_forward",
+           "improved_sampling", "register_plan"]
+
+# ------------------------------------------------------------------------------ plan registry (network-level ops)
+# Custom-op schemas carry tensors and scalars only, so the modules register their launch plans / sampler states here and
+# pass the integer id.  Weak references: a plan dies with the module cache that owns it.
+_PLAN_IDS = itertools.count(1)
+_PLANS: "weakref.WeakValueDictionary[int, object]" = weakref.WeakValueDictionary()
+
+
+def register_plan(obj) -> int:
+    pid = next(_PLAN_IDS)
+    _PLANS[pid] = obj
+    return pid
+
+
+def _lookup(pid: int):
+    obj = _PLANS.get(pid)
+    if obj is None:
+        raise RuntimeError(f"b200dn: launch plan {pid} no longer exists (its module was moved, reloaded or freed)")
+    return obj
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -120,7 +148,7 @@ def conv_in(x: torch.Tensor, t: Optional[torch.Tensor], weight: torch.Tensor, bi
     with torch.cuda.device(x.device):
         rc = _lib.lib().b200dn_conv_in(x.data_ptr(), Bx, _ptr(t), 1 if t is not None else 0, 0, 0, batch, H, W,
                                        weight.shape[0], weight.data_ptr(), bias.data_ptr(), slope.data_ptr(), prec,
-                                       out_hi.data_ptr(), _ptr(out_lo), out_hi.shape[-1], _stream(x))
+                                       out_hi.data_ptr(), _ptr(out_lo), out_hi.shape[-1], None, _stream(x))
     _lib.check(rc, "conv_in")
 
 
@@ -141,3 +169,34 @@ def sampler_step(x: torch.Tensor, u1: torch.Tensor, u2: torch.Tensor, y: torch.T
 @sampler_step.register_fake
 def _(x, u1, u2, y, one_m_at, at, one_m_ap, ap):
     return torch.empty_like(x)
+
+
+# ------------------------------------------------------------------------------ network-level ops (the product path)
+@torch.library.custom_op("b200dn::rdunet_forward", mutates_args=())
+def rdunet_forward(x: torch.Tensor, t: Optional[torch.Tensor], plan_id: int) -> torch.Tensor:
+    """RDUNet / RDUNet_T forward (UNet/RDUNet_model.py:157-186, diffusion_denoising/Unet/Unet_model.py:133-166) over a
+    registered :class:`rdunet.ForwardPlan`: fp32 NCHW in, fresh fp32 NCHW out."""
+    _cuda(x, t)
+    plan = _lookup(plan_id)
+    with torch.cuda.device(x.device):
+        return plan.forward(x, t)
+
+
+@rdunet_forward.register_fake
+def _(x, t, plan_id):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("b200dn::improved_sampling", mutates_args=())
+def improved_sampling(noisy: torch.Tensor, state_id: int) -> torch.Tensor:
+    """DiffusionModel.improved_sampling (diffusion_denoising/diffusion_RDUnet.py:38-50) over a registered sampler
+    state (2B-batched forwards + fused update step, one CUDA graph)."""
+    _cuda(noisy)
+    st = _lookup(state_id)
+    with torch.cuda.device(noisy.device):
+        return st.sample(noisy)
+
+
+@improved_sampling.register_fake
+def _(noisy, state_id):
+    return torch.empty_like(noisy)

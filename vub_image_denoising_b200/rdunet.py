@@ -23,7 +23,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, ops
 from ._lib import IgemmArgs
 
 __all__ = ["RDUNet", "RDUNet_T", "init_weights", "ForwardPlan", "DEFAULT_PREC"]
@@ -162,6 +162,12 @@ class _RDUNetBase(nn.Module):
         state["_plans"] = {}
         return state
 
+    def invalidate_plans(self) -> None:
+        """Drop every cached ForwardPlan (packed weights, bias / slope snapshots, captured graphs).  Needed only after
+        in-place parameter writes that bypass autograd's version counter (``p.data.copy_()``, ``p.data.mul_()``);
+        ``load_state_dict``, ``.to()`` and ordinary in-place ops are detected automatically."""
+        self._plans = {}
+
     # ---- helpers
     def _param_signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
@@ -209,8 +215,8 @@ class RDUNet(_RDUNetBase):
 
     def forward(self, inputs: torch.Tensor) -> torch.Tensor:
         x = self._check_input(inputs)
-        with torch.cuda.device(x.device):
-            return self.plan(x.size(0), x.size(2), x.size(3)).forward(x)
+        plan = self.plan(x.size(0), x.size(2), x.size(3))
+        return torch.ops.b200dn.rdunet_forward(x, None, plan.plan_id)
 
 
 class RDUNet_T(_RDUNetBase):
@@ -229,8 +235,8 @@ class RDUNet_T(_RDUNetBase):
         t = t.detach().to(device=x.device, dtype=torch.float32)
         # same broadcast as `t.expand(B, 1, H, W)` at Unet_model.py:135 (raises on incompatible shapes)
         t.expand(x.size(0), 1, x.size(2), x.size(3))
-        with torch.cuda.device(x.device):
-            return self.plan(x.size(0), x.size(2), x.size(3)).forward(x, t)
+        plan = self.plan(x.size(0), x.size(2), x.size(3))
+        return torch.ops.b200dn.rdunet_forward(x, t, plan.plan_id)
 
 
 # --------------------------------------------------------------------------- the launch plan
@@ -277,6 +283,13 @@ class ForwardPlan:
         self.out_channels = net._out_channels
         self.signature = None
         self._keep = []          # tensors referenced by raw pointer from the arg blocks
+        self._handles = None     # b200dn_igemm_prepared* per launch (encoded tensor maps + launch geometry)
+        self._ready = None       # event recorded after the weight-pack kernels of _build
+        self._ready_streams = set()
+        # fp16 storage saturates at +-65504 (cvt.rn.satfinite): every fp16 launch ORs 1 into this device flag when a
+        # stored value hit the limit, so a caller (the sampler) can detect it and retry at a wider precision
+        self.sat_flag = (torch.zeros(1, dtype=torch.int32, device=next(net.parameters()).device)
+                         if self.prec in _lib.FP16_PRECS else None)
         self.launches = []       # list[IgemmArgs]
         self.layer_info = []     # per launch: mode / shape / FLOPs (diagnostics)
         self.flops = 0
@@ -286,6 +299,7 @@ class ForwardPlan:
         dev = self.device
         with torch.cuda.device(dev):
             self._build(net)
+        self.plan_id = ops.register_plan(self)      # handle the torch.ops.b200dn.rdunet_forward custom op takes
 
     # ---- weights
     def _pack(self, conv: nn.Module, transposed: bool = False) -> torch.Tensor:
@@ -311,9 +325,10 @@ class ForwardPlan:
 
     @staticmethod
     def _f32(p: torch.Tensor, keep: list) -> int:
-        t = p.detach()
-        if t.dtype != torch.float32 or not t.is_contiguous():
-            t = t.float().contiguous()
+        """Plan-owned fp32 snapshot of a bias / PReLU-slope / ingest-weight parameter.  The packed conv weights are
+        copies too, so a plan is self-consistent even if the caller later writes the parameters in place without
+        bumping their version (EMA / weight averaging through ``p.data``); ``invalidate_plans()`` refreshes it."""
+        t = p.detach().to(torch.float32).contiguous().clone()
         keep.append(t)
         return t.data_ptr()
 
@@ -327,6 +342,8 @@ class ForwardPlan:
         hi, lo = src.ptrs()
         a.in_[0], a.in_[1] = hi, lo
         a.in_ctot = src.ctot
+        if self.sat_flag is not None:
+            a.sat_flag = self.sat_flag.data_ptr()
         a.wpacked = self._pack(conv, transposed).data_ptr()
         a.bias = self._f32(conv.bias, self._keep)
         a.slope = self._f32(actv.weight, self._keep)
@@ -401,7 +418,29 @@ class ForwardPlan:
         ob = net.output_block
         self._igemm(_lib.MODE_CONV3X3, ob.conv_1, ob.actv_1, Da[0], F, I0, 0, B, H, W)
         self.out_args = self._igemm(_lib.MODE_CONV3X3, ob.conv_2, ob.actv_2, I0, F, None, 0, B, H, W, nchw=True)
-        self._refs = [C.byref(a) for a in self.launches]
+        # prepare every launch once: validation, tiling plan and the 2-3 CUtensorMap encodes (~25 us of host time per
+        # layer when done per call) happen here; run() then costs one C call that enqueues the 68 kernels
+        n = len(self.launches)
+        self._handles = (C.c_void_p * n)()
+        for i, a in enumerate(self.launches):
+            if a.out_kind == _lib.OUT_NCHW32:      # bound per call in run(); prepare wants a non-null placeholder
+                a.out_nchw = self._keep[0].data_ptr()
+            h = C.c_void_p()
+            _lib.check(self.lib.b200dn_igemm_prepare(C.byref(a), C.byref(h)), f"igemm_prepare (launch {i})")
+            self._handles[i] = h
+        self._out_handle = self._handles[n - 1]
+        self._ready = torch.cuda.Event()
+        self._ready.record(torch.cuda.current_stream(self.device))
+
+    def __del__(self):
+        handles, self._handles = getattr(self, "_handles", None), None
+        if handles is not None:
+            try:
+                for h in handles:
+                    if h:
+                        self.lib.b200dn_igemm_release(h)
+            except Exception:   # interpreter shutdown
+                pass
 
     # ---- execution
     def forward(self, x: torch.Tensor, t: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -463,7 +502,12 @@ class ForwardPlan:
         (after the ingest conv, after the last igemm) — bench.py's live per-kernel timing.
         """
         lib = self.lib
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        cur = torch.cuda.current_stream(self.device)
+        stream = cur.cuda_stream
+        if stream not in self._ready_streams:
+            # the pack kernels ran on whichever stream was current when the plan was built: order this stream after them
+            cur.wait_event(self._ready)
+            self._ready_streams.add(stream)
         bx = x_batch or self.B
         if self.with_t:
             if t is not None:
@@ -477,24 +521,19 @@ class ForwardPlan:
         hi, lo = I0.ptrs()
         rc = lib.b200dn_conv_in(x.data_ptr(), bx, t_ptr, t_strides[0], t_strides[1], t_strides[2],
                                 self.B, self.H, self.W, self.F, self.in_w, self.in_b, self.in_s, self.prec,
-                                hi, lo, I0.ctot, stream)
+                                hi, lo, I0.ctot, self.sat_flag.data_ptr() if self.sat_flag is not None else None, stream)
         _lib.check(rc, "conv_in")
-        oa = self.out_args
-        oa.out_nchw = out.data_ptr()
-        oa.res_nchw = x.data_ptr()
-        oa.res_bmod = bx
-        igemm = lib.b200dn_igemm
+        _lib.check(lib.b200dn_igemm_rebind_nchw(self._out_handle, out.data_ptr(), x.data_ptr(), bx), "igemm_rebind_nchw")
         if events is not None:
             events[0].record()
         if layer_events is None:
-            for ref in self._refs:
-                rc = igemm(ref, stream)
-                if rc:
-                    _lib.check(rc, "igemm")
+            rc = lib.b200dn_igemm_launch_list(self._handles, len(self.launches), stream)
+            if rc:
+                _lib.check(rc, "igemm_launch_list")
         else:   # diagnostic: one event after every tensor-core launch (tools/layer_times.py)
             layer_events[0].record()
-            for i, ref in enumerate(self._refs):
-                _lib.check(igemm(ref, stream), "igemm")
+            for i in range(len(self.launches)):
+                _lib.check(lib.b200dn_igemm_launch(self._handles[i], stream), "igemm_launch")
                 layer_events[i + 1].record()
         if events is not None:
             events[1].record()
