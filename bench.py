@@ -11,8 +11,13 @@ RDUNet forward (1 CUDA-core ingest conv + 68 tcgen05 implicit-GEMM launches) -> 
 `value` is timed with the clean batch resident in HBM; `e2e` runs the same step from pinned HOST buffers
 with the H2D copy of the patches and the D2H copy of the denoised batch + metrics inside the timed region
 (copies on two side streams, double-buffered, so they overlap the neighbouring steps' compute).
-Each rank processes its own batch (weak scaling, no data-path collective); the metric sums are combined
-by one NCCL all-reduce per step.  A secondary key reports ms per diffusion sample (RDUNet_T(32), T=20).
+Each rank processes its own batch (weak scaling, NO collective inside the timed region: patches are independent
+units); every rank accumulates its metric sums on device and ONE NCCL all-reduce combines them after the timed
+region (SURVEY.md §8 e), so the N-GPU curve measures replica independence, not communication.
+The `diffusion` key carries the second half of BASELINE.json's metric, ms per diffusion sample
+(DiffusionModel(RDUNet_T(32), T=20).improved_sampling, 256x256): device-timed value, roofline, an end-to-end number
+from pinned host buffers, batch-1 latencies, and for N > 1 both the weak (16 samples per GPU) and the strong
+(16 samples split over the GPUs, BASELINE config 3) reading.
 """
 from __future__ import annotations
 
@@ -109,7 +114,8 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------ reference arm
 def cpu_reference_pass(base_filters: int, batch: int, threads: int, repeats: int, warmup: int, seed: int = 7):
     """The reference's CPU path for the same step on `batch` patches: numpy/PIL-style noise + RDUNet fp32 forward
-    (oracle port of the reference modules) + host PSNR/SSIM.  Returns (best seconds per step, MPix/s)."""
+    (oracle port of the reference modules) + host PSNR/SSIM.  Returns (seconds of every timed step, MPix/s from their
+    MEAN) — the same estimator for `cpu_baseline` and for the `--impl reference` arm."""
     from oracle import metrics_oracle, noise_oracle, rdunet_oracle
     import vub_image_denoising_b200 as b2
 
@@ -130,7 +136,7 @@ def cpu_reference_pass(base_filters: int, batch: int, threads: int, repeats: int
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
-    return times, batch * MPIX_PER_PATCH / min(times)
+    return times, batch * MPIX_PER_PATCH / float(np.mean(times))
 
 
 def run_reference(args) -> None:
@@ -152,11 +158,124 @@ def run_reference(args) -> None:
                    "reference's PyTorch modules in fp32 + numpy/scipy metrics) on the host cores; each step = 1 patch of the "
                    "64-patch batch (bounded sample)"},
         "cpu_baseline": {"value": value, "unit": "MPix/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_batch} patch per step, mean of {args.steps} steps"},
+                         "sample": f"{sample_batch} patch per step, mean of {args.steps} steps after "
+                                   f"{min(args.warmup, 1)} warm-up"},
         "e2e": {"value": value, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+
+# ------------------------------------------------------------------------------------ diffusion half of the metric
+DIFF_T = 20
+DIFF_F = 32
+# SURVEY.md §8 d: 40 forwards x 96.30 GFLOP, 40 x 425 MB of layer-by-layer 16-bit traffic per sample
+DIFF_FLOP_PER_SAMPLE = 40 * 96.30e9
+DIFF_BYTES_PER_SAMPLE = 40 * 425e6
+
+
+def _time_sampler(dm, noisy, reps, barrier):
+    import torch.distributed as dist
+    for _ in range(3):
+        dm.improved_sampling(noisy)
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(reps):
+        dm.improved_sampling(noisy)
+    d1.record()
+    barrier()
+    t = torch.tensor([d0.elapsed_time(d1) / reps], dtype=torch.float64, device=noisy.device)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def diffusion_metrics(b2, dev, world, rank, clean_dev, peaks, barrier):
+    """ms per diffusion sample: DiffusionModel(RDUNet_T(32), 20).improved_sampling on 256x256 (the reference's own
+    evaluation width, evaluate_model.py:103-105).  Device-timed (inputs resident), MAX over ranks."""
+    torch.manual_seed(7)
+    dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=DIFF_F), timesteps=DIFF_T).to(dev).eval()
+    dm.check_saturation = True        # the product default: one 4-byte flag read per call is inside the timing
+
+    def noisy_batch(n):
+        reps = (n + clean_dev.shape[0] - 1) // clean_dev.shape[0]
+        src = clean_dev.repeat(reps, 1, 1, 1)[:n].contiguous()
+        return b2.noise.add_gaussian_noise(src, 25.0, seed=5, return_u8=False)[1]
+
+    res = {"metric": "ms_per_diffusion_sample", "unit": "ms", "timesteps": DIFF_T,
+           "model": f"RDUNet_T(base_filters={DIFF_F})", "precision": dm.precision, "higher_is_better": False}
+    # (1) the BASELINE configuration on one GPU / weak reading on N GPUs: 16 samples per GPU
+    per_gpu = 16
+    noisy16 = noisy_batch(per_gpu)
+    ms16 = _time_sampler(dm, noisy16, 3, barrier)
+    res.update({"value": ms16 / per_gpu, "batch_per_gpu": per_gpu, "ms_per_batch": ms16,
+                "samples_per_s_all_gpus": world * per_gpu / (ms16 / 1e3), "scaling": "weak"})
+    # roofline: the slower of the tensor and the HBM time of a sample's algorithmic work
+    t_tensor = DIFF_FLOP_PER_SAMPLE / (peaks["bf16_tflops"] * 1e12)
+    t_hbm = DIFF_BYTES_PER_SAMPLE / (peaks["hbm_gbs"] * 1e9)
+    bound = "tensor" if t_tensor >= t_hbm else "hbm"
+    t_s = ms16 / per_gpu / 1e3
+    if bound == "tensor":
+        ach, peak, unit = DIFF_FLOP_PER_SAMPLE / t_s / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+    else:
+        ach, peak, unit = DIFF_BYTES_PER_SAMPLE / t_s / 1e9, peaks["hbm_gbs"], "GB/s"
+    res["roofline"] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                       "roofline_ms_per_sample": max(t_tensor, t_hbm) * 1e3, "tensor_ms_per_sample": t_tensor * 1e3,
+                       "hbm_ms_per_sample": t_hbm * 1e3, "hbm_gbs_achieved": DIFF_BYTES_PER_SAMPLE / t_s / 1e9,
+                       "algorithmic_flops_per_sample": DIFF_FLOP_PER_SAMPLE,
+                       "algorithmic_bytes_per_sample": DIFF_BYTES_PER_SAMPLE, "peak_source": peaks["source"],
+                       "traffic": None, "kernels": "40 x (conv_in + 68 tcgen05 launches) + 20 x sampler_step per sample batch, "
+                                                   "one CUDA graph; per-layer ncu captures under profiles/"}
+    # (2) end to end through the public call with HOST buffers: pinned noisy batch -> H2D -> improved_sampling -> D2H
+    host_in = noisy16.cpu().pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    for _ in range(2):
+        host_out.copy_(dm.improved_sampling(host_in.to(dev, non_blocking=True)), non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        x = host_in.to(dev, non_blocking=True)
+        host_out.copy_(dm.improved_sampling(x), non_blocking=True)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res["e2e"] = {"value": float(t[0]) / per_gpu, "unit": "ms", "ms_per_batch": float(t[0]),
+                  "h2d_bytes_per_step": int(host_in.numel() * 4), "d2h_bytes_per_step": int(host_out.numel() * 4)}
+    # (3) strong reading for N > 1 (BASELINE config 3: 16 samples split by batch over the GPUs)
+    if world > 1:
+        n_loc = max(1, 16 // world)
+        ms_s = _time_sampler(dm, noisy_batch(n_loc), 3, barrier)
+        res["strong"] = {"scaling": "strong", "samples_total": n_loc * world, "batch_per_gpu": n_loc, "ms_per_batch": ms_s,
+                         "ms_per_sample_per_gpu": ms_s / n_loc, "samples_per_s_all_gpus": world * n_loc / (ms_s / 1e3)}
+    # (4) batch 1: the reference's own call pattern (evaluate_model.py:318, evaluate_SIDD.py:116, benchmark.py:82-90)
+    ms1 = _time_sampler(dm, noisy_batch(1), 5, barrier)
+    res["batch1"] = {"sampler_ms_per_sample": ms1,
+                     "sampler_frac_of_roofline": max(t_tensor, t_hbm) * 1e3 / ms1}
+    del dm
+    torch.manual_seed(7)
+    net = b2.RDUNet(base_filters=128).to(dev).eval()
+    x1 = noisy_batch(1)
+    with torch.no_grad():
+        for _ in range(4):
+            net(x1)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(20):
+            net(x1)
+        f1.record()
+        barrier()
+    ms_f = f0.elapsed_time(f1) / 20
+    res["batch1"].update({"rdunet128_forward_ms": ms_f, "rdunet128_tflops": 1537.43e9 / (ms_f / 1e3) / 1e12,
+                          "rdunet128_mpix_per_s": MPIX_PER_PATCH / (ms_f / 1e3)})
+    return res
 
 
 # ------------------------------------------------------------------------------------ B200 arm
@@ -303,14 +422,16 @@ def run_b200(args) -> None:
     achieved = igemm_flops / (igemm_last_ms / 1e3) / 1e12
     # DRAM traffic of the same 68 launches from the committed ncu pass over this command (profiles/), per launch
     traffic = None
-    summ = ROOT / "profiles" / "r01_bench_launches_summary.json"
+    summ = ROOT / "profiles" / "r02_bench_launches_summary.json"
+    if not summ.exists():
+        summ = ROOT / "profiles" / "r01_bench_launches_summary.json"
     if summ.exists() and F == 128 and B == 64:
         traffic = json.loads(summ.read_text())["tensor_core_kernels"]["dram_bytes_per_launch"]
     roofline = {"bound": "tensor", "kernel": "conv3x3_slab2_kernel (cta_group::2) + conv3x3_slab_kernel + igemm_kernel "
                                              "(68 tcgen05 launches per step)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-                "traffic_note": "dram__bytes_read+write per launch, mean over the 68 launches (ncu, profiles/r01_bench_launches.csv); "
+                "traffic_note": f"dram__bytes_read+write per launch, mean over the 68 launches (ncu, profiles/{summ.name}); "
                                 "algorithmic layer-by-layer bytes are 1.83 GB per launch, so L2 already absorbs re-reads",
                 "peak_source": peaks["source"],
                 "algorithmic_flops_per_step": igemm_flops, "kernel_ms_per_step": igemm_last_ms,
@@ -334,30 +455,10 @@ def run_b200(args) -> None:
         "quality": {"mean_psnr_db": red["psnr"], "mean_ssim": red["ssim"], "images": red["count"]},
     }
 
-    # ---------------- secondary metric: ms per diffusion sample (RDUNet_T(32), T = 20, batch 16 split over the GPUs)
+    # ---------------- second half of the metric: ms per diffusion sample (RDUNet_T(32), T = 20, 256x256)
     if not args.skip_diffusion:
         del plan, out, net
-        b2_local = max(1, 16 // world)
-        torch.manual_seed(7)
-        dm = b2.DiffusionModel(b2.RDUNet_T(base_filters=32), timesteps=20).to(dev).eval()
-        _, noisy, _ = b2.noise.add_gaussian_noise(clean_dev[:b2_local].contiguous(), 25.0, seed=5, return_u8=False)
-        for _ in range(2):
-            dm.improved_sampling(noisy)
-        barrier()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
-        d0.record()
-        for _ in range(reps):
-            dm.improved_sampling(noisy)
-        d1.record()
-        barrier()
-        d_ms = torch.tensor([d0.elapsed_time(d1) / reps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(d_ms, op=dist.ReduceOp.MAX)
-        line["diffusion"] = {"metric": "ms_per_diffusion_sample", "value": float(d_ms[0]) / b2_local, "unit": "ms",
-                             "batch_per_gpu": b2_local, "ms_per_batch": float(d_ms[0]), "timesteps": 20,
-                             "model": "RDUNet_T(base_filters=32)", "precision": dm.precision,
-                             "samples_per_s_all_gpus": world * b2_local / (float(d_ms[0]) / 1e3)}
+        line["diffusion"] = diffusion_metrics(b2, dev, world, rank, clean_dev, peaks, barrier)
 
     # ---------------- CPU baseline (rank 0, N = 1 only): the oracle port on the host cores, bounded sample
     if rank == 0 and world == 1 and not args.skip_cpu:
@@ -365,7 +466,8 @@ def run_b200(args) -> None:
         times, mpix = cpu_reference_pass(F, 1, cores, repeats=2, warmup=1)
         line["cpu_baseline"] = {"value": mpix, "unit": "MPix/s", "cores": cores, "kind": "port",
                                 "sample": f"1 of the {B} patches per step (RDUNet({F}) fp32 forward + noise + PSNR/SSIM), "
-                                          f"best of 2 after 1 warm-up, {min(times):.2f} s"}
+                                          f"mean of 2 steps after 1 warm-up, {float(np.mean(times)):.2f} s per step "
+                                          "(same estimator as --impl reference)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -4,42 +4,16 @@ oracle/pin_against_reference.py from the real reference modules) and against the
 Bars (BASELINE.json north_star): bf16 path >= 99.9 % of pixels within 1/255 in [0,1] space and PSNR within
 0.02 dB; fp32 validation build (bf16x3) <= 1e-4 max abs error.
 """
-import math
-
 import numpy as np
 import pytest
 import torch
 
-from helpers import PIX_TOL, sd_digest
+from helpers import check_bar as _check_bar, sd_digest
 import vub_image_denoising_b200 as b2
 from oracle import rdunet_oracle as orc
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-
-
-def _frac_within(a: torch.Tensor, b: torch.Tensor) -> float:
-    return float(((a - b).abs() <= PIX_TOL).double().mean())
-
-
-def _psnr_db(ref: torch.Tensor, x: torch.Tensor, data_range=2.0) -> float:
-    mse = float(((ref.double() - x.double()) ** 2).mean())
-    return 10 * math.log10(data_range ** 2 / mse)
-
-
-def _check_bar(got, ref, clean=None, what=""):
-    """North-star bar: >= 99.9 % of output values within 1/255 (and PSNR within 0.02 dB when `clean` is given).
-    The golden micro-cases have ~1.5k values, where 0.1 % is 1.5 values: there the bar reads 'at most 2 values
-    outside'; the BASELINE-size tests below (196k values per patch) apply the percentage as written."""
-    frac = _frac_within(got, ref)
-    mx = float((got - ref).abs().max())
-    n_bad = int(((got - ref).abs() > PIX_TOL).sum())
-    ok = frac >= 0.999 or (got.numel() < 4000 and n_bad <= 2)
-    assert ok, f"{what}: only {frac * 100:.3f}% of pixels within 1/255 ({n_bad} outside, max err {mx:.3e})"
-    if clean is not None:
-        d = abs(_psnr_db(clean, got) - _psnr_db(clean, ref))
-        assert d <= 0.02, f"{what}: PSNR differs by {d:.4f} dB"
-    return frac, mx
 
 
 @pytest.mark.parametrize("precision,max_abs", [("bf16", None), ("fp16", None), ("bf16x2", None), ("bf16x3", 1e-4)])

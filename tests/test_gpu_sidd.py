@@ -95,3 +95,44 @@ def test_submission_csv_round_trip_of_device_output(built_lib, tmp_path):
         idx, s = line.split(",", 1)
         assert int(idx) == k
         assert np.array_equal(sidd.base64string_to_array(s, np.uint8, (16, 16, 3)), out[0, k])
+
+
+def test_benchmark_script_flow_through_the_shim(built_lib, tmp_path):
+    """The statement sequence of evaluate_SIDD/benchmark.py (:15-27 import + checkpoint load, :32-46 one-argument
+    denoiser, :79-103 block loop + DataFrame.to_csv) on top of the shim, next to the batched path."""
+    import pandas as pd
+    b2.shim.install()
+    try:
+        from diffusion_denoising.diffusion_RDUnet import RDUNet_T, DiffusionModel
+        torch.manual_seed(3)
+        trained = DiffusionModel(RDUNet_T(base_filters=16), timesteps=2)
+        ckpt = tmp_path / "diffusion_RDUnet_model_checkpointed_epoch_43.pth"
+        torch.save({"epoch": 43, "model_state_dict": trained.state_dict()}, ckpt)       # the reference's checkpoint format
+        device = torch.device("cuda")
+        model = DiffusionModel(RDUNet_T(base_filters=16), timesteps=2).to(device)
+        checkpoint = torch.load(ckpt, map_location=device)
+        model.load_state_dict(checkpoint["model_state_dict"])
+        model.eval()
+        b2.shim.install(model=model)
+        rng = np.random.default_rng(2)
+        inputs = rng.integers(0, 256, size=(2, 2, 32, 32, 3), dtype=np.uint8)
+        strings = []
+        for i in range(inputs.shape[0]):
+            for j in range(inputs.shape[1]):
+                in_block = inputs[i, j, :, :, :]
+                out_block = sidd.my_srgb_denoiser(in_block)                                  # one-argument form
+                assert in_block.shape == out_block.shape and in_block.dtype == out_block.dtype
+                strings.append(sidd.array_to_base64string(out_block))
+        df = pd.DataFrame()
+        df["ID"] = np.arange(len(strings))
+        df["BLOCK"] = strings
+        ref_csv = tmp_path / "ref.csv"
+        df.to_csv(ref_csv, index=False)
+        ours = tmp_path / "SubmitSrgb.csv"
+        sidd.write_submission_csv(str(ours), sidd.denoise_blocks_srgb(model, inputs, batch=4))
+        assert ours.read_bytes() == ref_csv.read_bytes()
+    finally:
+        sidd.set_default_model(None)
+        b2.shim.uninstall()
+    with pytest.raises(RuntimeError, match="no model registered"):
+        sidd.my_srgb_denoiser(inputs[0, 0])

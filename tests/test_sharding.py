@@ -108,3 +108,44 @@ def test_world_size_2_gloo():
             p.join(timeout=180)
         assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
         assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def _subgroup_worker(rank, world, port, ret):
+    """3 processes; the tiled image is denoised by the sub-group {1, 2} and stitched on group rank 1 = global rank 2."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sub = dist.new_group(ranks=[1, 2])
+        g = torch.Generator().manual_seed(0)
+        img = torch.rand(1, 3, 96, 160, generator=g)
+        if rank in (1, 2):
+            out = sh.denoise_tiled(_local_net, img, rows=2, cols=4, halo=16, dst=1, group=sub)
+            if rank == 2:
+                assert torch.equal(out, _local_net(img))
+            else:
+                assert out is None
+            acc = sh.MetricAccumulator("cpu")
+            acc.update(torch.tensor([10.0 * rank]), torch.tensor([0.5]))
+            red = acc.reduce(group=sub)
+            assert red["count"] == 2 and abs(red["psnr"] - 15.0) < 1e-12
+            with pytest.raises(ValueError):
+                sh.denoise_tiled(_local_net, img, rows=1, cols=2, halo=16, dst=2, group=sub)
+        ret[rank] = "ok"
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tiled_stitch_on_a_subgroup_gloo():
+    world = 3
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        procs = [ctx.Process(target=_subgroup_worker, args=(r, world, port, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=180)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        assert dict(ret) == {0: "ok", 1: "ok", 2: "ok"}

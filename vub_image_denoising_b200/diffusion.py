@@ -63,14 +63,17 @@ class _SamplerState:
         self.xa = torch.empty_like(self.y)
         self.xb = torch.empty_like(self.y)
         self.u = torch.empty((2 * B, 3, H, W), dtype=torch.float32, device=dev)
-        # per step: B copies of fl32(t/T) then B copies of fl32((t-1)/T)  (diffusion_RDUnet.py:43,46)
-        rows = []
+        # per step: B copies of fl32(t/T) then B copies of fl32((t-1)/T)  (diffusion_RDUnet.py:43,46).  Built with
+        # device ops (an fp64 quotient rounded to fp32 is what torch.tensor([t / T]) holds) so that a first call made
+        # inside a caller's graph capture needs no pageable H2D copy.
         self.coef = []
         for t in range(T, 0, -1):
             a_t, a_p = t / T, (t - 1) / T
-            rows.append([_f32(a_t)] * B + [_f32(a_p)] * B)
             self.coef.append((_f32(1 - a_t), _f32(a_t), _f32(1 - a_p), _f32(a_p)))
-        self.t_all = torch.tensor(rows, dtype=torch.float32, device=dev).contiguous()
+        steps = torch.arange(T, 0, -1, dtype=torch.float64, device=dev)
+        a_t32 = (steps / T).to(torch.float32).view(T, 1).expand(T, B)
+        a_p32 = ((steps - 1) / T).to(torch.float32).view(T, 1).expand(T, B)
+        self.t_all = torch.cat([a_t32, a_p32], dim=1).contiguous()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.result = self.y  # set by _enqueue
         self.state_id = ops.register_plan(self)     # handle the torch.ops.b200dn.improved_sampling custom op takes

@@ -504,7 +504,7 @@ class ForwardPlan:
         lib = self.lib
         cur = torch.cuda.current_stream(self.device)
         stream = cur.cuda_stream
-        if stream not in self._ready_streams:
+        if stream not in self._ready_streams and not torch.cuda.is_current_stream_capturing():
             # the pack kernels ran on whichever stream was current when the plan was built: order this stream after them
             cur.wait_event(self._ready)
             self._ready_streams.add(stream)

@@ -133,13 +133,22 @@ def tiles_of_rank(tiles: Sequence[Tile], rank: int, world: int) -> List[Tile]:
 def denoise_tiled(fn: Callable[[torch.Tensor], torch.Tensor], image: torch.Tensor, rows: int, cols: int,
                   halo: int = RF_HALO, dst: int = 0, group=None) -> Optional[torch.Tensor]:
     """Denoise one large image ``[B, 3, H, W]`` tile by tile; with torch.distributed initialised the tiles
-    are dealt round-robin to ranks and the interiors are sent to rank `dst`, which returns the stitched
-    image (other ranks return None).  Every rank must hold the same input `image` (it is tiny next to
-    the activations: 100 MB for 4K fp32)."""
+    are dealt round-robin to the ranks of `group` and the interiors are sent to rank `dst`, which returns the
+    stitched image (other ranks return None).  `dst` is a rank WITHIN `group` (== the global rank for the default
+    group); the point-to-point calls translate group ranks to the global ranks ``isend`` / ``irecv`` expect.
+    Every rank must hold the same input `image` (it is tiny next to the activations: 100 MB for 4K fp32)."""
     B, Cn, H, W = image.shape
     tiles = plan_tiles(H, W, rows, cols, halo)
     world = dist.get_world_size(group) if _dist_on() else 1
     rank = dist.get_rank(group) if _dist_on() else 0
+    if rank < 0:
+        raise RuntimeError("denoise_tiled: this process is not a member of `group`")
+    if not 0 <= dst < world:
+        raise ValueError(f"dst={dst} is not a rank of the {world}-rank group")
+
+    def global_rank(r: int) -> int:
+        return r if group is None else dist.get_global_rank(group, r)
+
     mine = tiles_of_rank(tiles, rank, world)
     interiors = {}
     for t in mine:
@@ -161,12 +170,12 @@ def denoise_tiled(fn: Callable[[torch.Tensor], torch.Tensor], image: torch.Tenso
                 full[:, :, t.y0:t.y1, t.x0:t.x1] = interiors[t.index]
             else:
                 buf = torch.empty((B, Cn, t.y1 - t.y0, t.x1 - t.x0), dtype=image.dtype, device=image.device)
-                pending.append((t, buf, dist.irecv(buf, src=owner, group=group, tag=t.index)))
+                pending.append((t, buf, dist.irecv(buf, src=global_rank(owner), group=group, tag=t.index)))
         for t, buf, work in pending:
             work.wait()
             full[:, :, t.y0:t.y1, t.x0:t.x1] = buf
         return full
-    works = [dist.isend(interiors[t.index], dst=dst, group=group, tag=t.index) for t in mine]
+    works = [dist.isend(interiors[t.index], dst=global_rank(dst), group=group, tag=t.index) for t in mine]
     for w in works:
         w.wait()
     return None

@@ -27,9 +27,15 @@ def _module(name: str, **attrs) -> types.ModuleType:
     return m
 
 
-def install(force: bool = False) -> None:
-    """Register the aliases. Existing non-shim modules are left alone unless force=True."""
+def install(force: bool = False, model=None) -> None:
+    """Register the aliases. Existing non-shim modules are left alone unless force=True.
+    ``model``: optional module to bind as the global model of the one-argument ``sidd.my_srgb_denoiser(x)``
+    (the reference keeps it in a script-level global, evaluate_SIDD/benchmark.py:23-32)."""
     import torch
+
+    if model is not None:
+        from . import sidd
+        sidd.set_default_model(model)
 
     device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
     mods = {
