@@ -31,6 +31,8 @@
  *                                                                    evaluate_SIDD/evaluate_SIDD.py:63
  *   b200dn_ssim             skimage structural_similarity call sites evaluate_Unet_diffusion/evaluate_model.py:30-34,
  *                                                                    evaluate_SIDD/evaluate_SIDD.py:64
+ *   b200dn_welch_psd        scipy.signal.welch(img.flatten(), nperseg=256)
+ *                                                                    evaluate_Unet_diffusion/plot.py:155-157,233-235,287-290
  *   b200dn_gauss_noise_u8   np.random.normal + clip + uint8 + ToTensor/Normalize
  *                                                                    dataset_creation/custom_dataset.py:83-87,
  *                                                                    dataset_creation/data_loader.py:35-38
@@ -184,15 +186,28 @@ int b200dn_sampler_step(const float* x, const float* u1, const float* u2, const 
 int b200dn_lerp(const float* clean, const float* noisy, float alpha, float one_m_alpha,
                 float* out, int64_t n, void* stream);
 
-/* ---- metrics ------------------------------------------------------------------ */
+/* ---- metrics ------------------------------------------------------------------
+ * Both reductions are two-pass and bit-reproducible: every block writes one partial sum into `workspace`
+ * (device memory, 8-byte aligned, at least b200dn_*_workspace_bytes() bytes, contents undefined afterwards)
+ * and a second kernel adds the partials of each image / plane in a fixed order.  No atomics.          */
+int64_t b200dn_psnr_sse_workspace_bytes(int64_t n_images, int64_t n_per_image);
+int64_t b200dn_ssim_workspace_bytes(int64_t n_planes, int H, int W);
 /* sse[i] (fp64) = sum over the n_per_image elements of image i of (a-b)^2            */
 int b200dn_psnr_sse(const float* a, const float* b, int64_t n_images, int64_t n_per_image,
-                    double* sse, void* stream);
+                    double* sse, void* workspace, int64_t workspace_bytes, void* stream);
 /* skimage-0.22-style SSIM (7x7 uniform window, sample covariance, crop 3, K1=.01 K2=.03)
    on fp32 planes: a,b are [n_planes,H,W]; ssim_sum[p] (fp64) = sum of S over the cropped
-   interior of plane p (divide by (H-6)*(W-6) for the mean).                           */
+   interior of plane p (divide by (H-6)*(W-6) for the mean).  Window sums in fp32.     */
 int b200dn_ssim(const float* a, const float* b, int64_t n_planes, int H, int W,
-                float data_range, double* ssim_sum, void* stream);
+                float data_range, double* ssim_sum, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Welch PSD with scipy.signal.welch's defaults at nperseg = 256 (fs = 1, periodic Hann, 50 % overlap, constant
+   detrend, one-sided density scaling, mean over segments), float32 throughout like scipy for float32 input.
+   x: [n_signals, n] fp32 (each row one flattened image, n >= 256); pxx: [n_signals, 129] fp32;
+   frequencies are k/256, k = 0..128.  Two-pass, bit-reproducible (workspace as for the metrics above).  */
+int64_t b200dn_welch_psd_workspace_bytes(int64_t n_signals, int64_t n);
+int b200dn_welch_psd(const float* x, int64_t n_signals, int64_t n, float* pxx,
+                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- noise synthesis / data formats ------------------------------------------- */
 /* clean_u8: [B,H,W,C] uint8 (HWC as in PIL / the SIDD .mat blocks).

@@ -33,6 +33,53 @@ def test_psnr_ssim_match_oracle(shape, data_range, built_lib):
         assert float(ssim[i]) == pytest.approx(want_s, abs=1e-5)
 
 
+def test_metric_sums_are_bit_reproducible(built_lib):
+    """Two-pass fixed-order reductions: repeated calls give identical bits (the atomicAdd version did not), and a
+    batch-64 call equals the per-image calls bit for bit."""
+    a, b = _images(64, 3, 256, 256, seed=5)
+    A, B = a.to(DEV), b.to(DEV)
+    p0, s0 = b2.metrics.batch_metrics(A, B, 1.0)
+    for _ in range(5):
+        p1, s1 = b2.metrics.batch_metrics(A, B, 1.0)
+        assert torch.equal(p0, p1) and torch.equal(s0, s1)
+    sse_all = b2.metrics.batch_sse(A, B)
+    ss_all = b2.metrics.batch_ssim_planes(A.view(-1, 256, 256), B.view(-1, 256, 256), 1.0)
+    for i in (0, 31, 63):
+        assert torch.equal(b2.metrics.batch_ssim_planes(A[i], B[i], 1.0), ss_all[3 * i:3 * i + 3])
+    assert torch.isfinite(sse_all).all()
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 256, 256), (3, 1, 40, 52), (1, 3, 16, 16), (2, 3, 64, 67)])
+def test_welch_psd_matches_scipy(shape, built_lib):
+    """f4: the Welch PSD of flattened images (plot.py:155-157) against scipy.signal.welch itself."""
+    from oracle import psd_oracle as po
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(*shape, generator=g) * 2 - 1
+    x[0] = torch.nn.functional.avg_pool2d(x[0:1], 3, stride=1, padding=1)[0]      # one image-like (low-passed) case
+    f, pxx = b2.metrics.welch(x.to(DEV).flatten(1))
+    assert pxx.shape == (shape[0], 129) and pxx.dtype == torch.float32
+    for i in range(shape[0]):
+        rf, rp = po.welch_flat(x[i].numpy())
+        assert np.array_equal(f, rf) and rp.dtype == np.float32
+        got = pxx[i].cpu().numpy()
+        assert np.max(np.abs(got - rp)) <= 2e-5 * np.max(rp), f"image {i}: PSD differs from scipy by {np.max(np.abs(got - rp)):.3e}"
+        assert np.max(np.abs(got - rp) / np.maximum(rp, 1e-12)) <= 2e-3
+    # a single flattened image (the reference's call shape), and bit-reproducibility
+    f1, p1 = b2.metrics.welch(x[0].to(DEV).flatten())
+    assert p1.shape == (129,) and torch.equal(p1, pxx[0])
+    with pytest.raises(ValueError):
+        b2.metrics.welch(torch.zeros(100, device=DEV))
+
+
+def test_high_frequency_psd_mae_matches_plot_py(built_lib):
+    from oracle import psd_oracle as po
+    a, b = _images(3, 3, 128, 128, seed=9, noise=0.2)
+    got = b2.metrics.high_frequency_psd_mae(a.to(DEV), b.to(DEV)).cpu().numpy()
+    for i in range(3):
+        want = po.high_frequency_psd_mae(a[i].numpy(), b[i].numpy())
+        assert got[i] == pytest.approx(want, rel=1e-3)
+
+
 def test_reference_shaped_metric_calls(built_lib):
     a, b = _images(1, 3, 64, 64, seed=2)
     A, B = a[0].to(DEV), b[0].to(DEV)

@@ -1,0 +1,6 @@
+set -x
+cd $GRAFT_REPO_ROOT
+python -m pytest tests/test_gpu_metrics_noise.py tests/test_gpu_sidd.py -m gpu -x -q > gpurun_out/r02_pytest_metrics2.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_pytest_metrics2.log
+tail -30 gpurun_out/r02_pytest_metrics2.log
+python tools/hbm_kernels_bench.py > gpurun_out/r02_hbm_kernels2.log 2>&1
+cat gpurun_out/r02_hbm_kernels2.log

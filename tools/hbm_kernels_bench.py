@@ -40,6 +40,7 @@ x, u1, u2, y = (torch.rand(B, 3, 256, 256, device=dev) for _ in range(4))
 report("sampler_step (4 reads + 1 write fp32)", timeit(lambda: torch.ops.b200dn.sampler_step(x, u1, u2, y, 0.3, 0.7, 0.35, 0.65)), 5 * 4 * n)
 report("psnr sse (2 reads fp32)", timeit(lambda: b2.metrics.batch_sse(x, y)), 2 * 4 * n)
 report("ssim (2 reads fp32)", timeit(lambda: b2.metrics.batch_ssim_planes(x.view(-1, 256, 256), y.view(-1, 256, 256), 1.0)), 2 * 4 * n)
+report("welch psd nperseg=256 (1 read fp32, 129 floats out / image)", timeit(lambda: b2.metrics.welch(x.flatten(1))), 4 * n)
 clean_u8 = torch.randint(0, 256, (B, 256, 256, 3), dtype=torch.uint8, device=dev)
 sig = torch.full((B,), 25.0, device=dev)
 report("gauss_noise_u8 (1 B read, u8 + 2 fp32 written)", timeit(lambda: b2.noise.add_gaussian_noise(clean_u8, sig, seed=1)), n * (1 + 1 + 4 + 4))

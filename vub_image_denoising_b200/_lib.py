@@ -29,7 +29,8 @@ EXPORTS = (
     "b200dn_igemm", "b200dn_igemm_plan", "b200dn_igemm_prepare", "b200dn_igemm_rebind_nchw", "b200dn_igemm_launch",
     "b200dn_igemm_launch_list", "b200dn_igemm_release", "b200dn_conv_in",
     "b200dn_sampler_step", "b200dn_lerp",
-    "b200dn_psnr_sse", "b200dn_ssim",
+    "b200dn_psnr_sse", "b200dn_ssim", "b200dn_psnr_sse_workspace_bytes", "b200dn_ssim_workspace_bytes",
+    "b200dn_welch_psd", "b200dn_welch_psd_workspace_bytes",
     "b200dn_gauss_noise_u8", "b200dn_philox_normal", "b200dn_u8_to_norm", "b200dn_norm_to_u8",
 )
 
@@ -110,15 +111,24 @@ def lib() -> C.CDLL:
     L.b200dn_conv_in.argtypes = [vp, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp]
     L.b200dn_sampler_step.argtypes = [vp, vp, vp, vp, f32, f32, f32, f32, vp, i64, vp]
     L.b200dn_lerp.argtypes = [vp, vp, f32, f32, vp, i64, vp]
-    L.b200dn_psnr_sse.argtypes = [vp, vp, i64, i64, vp, vp]
-    L.b200dn_ssim.argtypes = [vp, vp, i64, i32, i32, f32, vp, vp]
+    L.b200dn_psnr_sse.argtypes = [vp, vp, i64, i64, vp, vp, i64, vp]
+    L.b200dn_ssim.argtypes = [vp, vp, i64, i32, i32, f32, vp, vp, i64, vp]
+    L.b200dn_psnr_sse_workspace_bytes.restype = i64
+    L.b200dn_psnr_sse_workspace_bytes.argtypes = [i64, i64]
+    L.b200dn_ssim_workspace_bytes.restype = i64
+    L.b200dn_ssim_workspace_bytes.argtypes = [i64, i32, i32]
+    L.b200dn_welch_psd.argtypes = [vp, i64, i64, vp, vp, i64, vp]
+    L.b200dn_welch_psd_workspace_bytes.restype = i64
+    L.b200dn_welch_psd_workspace_bytes.argtypes = [i64, i64]
     L.b200dn_gauss_noise_u8.argtypes = [vp, i32, i32, i32, i32, vp, C.c_uint64, C.c_uint32, vp, vp, vp, vp]
     L.b200dn_philox_normal.argtypes = [vp, i64, C.c_uint64, C.c_uint32, vp]
     L.b200dn_u8_to_norm.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.b200dn_norm_to_u8.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
-        if name not in ("b200dn_last_error", "b200dn_packed_weight_bytes", "b200dn_igemm_release"):
+        if name not in ("b200dn_last_error", "b200dn_packed_weight_bytes", "b200dn_igemm_release",
+                        "b200dn_psnr_sse_workspace_bytes", "b200dn_ssim_workspace_bytes",
+                        "b200dn_welch_psd_workspace_bytes"):
             fn.restype = i32
     if L.b200dn_abi_version() != ABI_VERSION:
         raise RuntimeError("libb200dn.so ABI version mismatch; rebuild the library")

@@ -1,10 +1,14 @@
-// metrics.cu — on-device PSNR / SSIM reductions (warp-shuffle + 128-bit loads).
+// metrics.cu — on-device PSNR / SSIM reductions (128-bit loads, warp-shuffle block sums, fixed-order final sums).
 //   PSNR: mse = mean((X-Y)^2); 10*log10(R^2/mse)          evaluate_Unet_diffusion/evaluate_model.py:36-41,
 //                                                         evaluate_SIDD/evaluate_SIDD.py:63 (skimage PSNR)
 //   SSIM: skimage.metrics.structural_similarity defaults   evaluate_Unet_diffusion/evaluate_model.py:30-34,
 //         (scikit-image==0.22.0, requirements.txt:98)      evaluate_SIDD/evaluate_SIDD.py:64
 // The kernels return raw sums (fp64); the host-side mirror turns them into dB / means, so a sharded run
 // can all-reduce the sums.
+//
+// Reproducibility: every block writes ONE partial sum to a caller-provided workspace and a second kernel adds the
+// partials of an image / plane in a fixed order, so the sums are bit-identical from run to run (the first version's
+// atomicAdd(double) across blocks was not).
 #include "common.cuh"
 
 namespace b200dn {
@@ -31,11 +35,25 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;  // valid in warp 0
 }
 
-constexpr int SSE_THREADS = 256;
+// out[i] = sum of partial[i * n_part + k], k = 0 .. n_part-1, in a fixed order (one warp per output).
+__global__ void __launch_bounds__(128) sum_partials_kernel(const double* __restrict__ partial, int n_part, int64_t n_out,
+                                                           double* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (i >= n_out) return;
+  const int lane = threadIdx.x & 31;
+  const double* p = partial + i * n_part;
+  double s = 0.0;
+  for (int k = lane; k < n_part; k += 32) s += p[k];
+  s = warp_sum(s);
+  if (lane == 0) out[i] = s;
+}
 
-// grid = (chunks, n_images); each block reduces a contiguous chunk of one image, one atomicAdd(double) per block.
+constexpr int SSE_THREADS = 256;
+constexpr int SSE_MAX_CHUNKS = 1024;
+
+// grid = (chunks, n_images); each block reduces a strided share of one image into one partial.
 __global__ void __launch_bounds__(SSE_THREADS) sse_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                          int64_t n_per_image, int vec_ok, double* __restrict__ sse) {
+                                                          int64_t n_per_image, int vec_ok, double* __restrict__ partial) {
   __shared__ double red[SSE_THREADS / 32];
   const int64_t img = blockIdx.y;
   const float* pa = a + img * n_per_image;
@@ -73,171 +91,223 @@ __global__ void __launch_bounds__(SSE_THREADS) sse_kernel(const float* __restric
   }
   dacc += static_cast<double>(acc0) + static_cast<double>(acc1) + static_cast<double>(acc2) + static_cast<double>(acc3);
   const double t = block_sum<SSE_THREADS>(dacc, red);
-  if (threadIdx.x == 0) atomicAdd(sse + img, t);
+  if (threadIdx.x == 0) partial[img * gridDim.x + blockIdx.x] = t;
+}
+
+int sse_chunks(int64_t n_images, int64_t n_per_image, int sms) {
+  // enough blocks per image to cover the machine ~4x, at least 4 float4 per thread
+  int64_t chunks = cdiv64(n_per_image / 4, static_cast<int64_t>(SSE_THREADS) * 4);
+  const int64_t want = cdiv64(static_cast<int64_t>(sms) * 16, n_images);
+  if (chunks > want) chunks = want;
+  if (chunks > SSE_MAX_CHUNKS) chunks = SSE_MAX_CHUNKS;
+  if (chunks < 1) chunks = 1;
+  return static_cast<int>(chunks);
 }
 
 // ------------------------------------------------------------------ SSIM
-// Tile of TS x TS interior outputs per block; needs a (TS+6)^2 input halo.  Follows skimage 0.22:
-// uniform_filter (7 taps, axis 0 then axis 1, each pass accumulated in double and rounded to float32),
-// cov_norm = 49/48, float32 elementwise math in skimage's operation order, crop 3, float64 sum.
-constexpr int TS = 32;
-constexpr int HALO = 6;
-constexpr int IN_T = TS + HALO;  // 38
-constexpr int SSIM_THREADS = 160;   // 152 vertical / 128 horizontal strip tasks per 32x32 tile
-constexpr double kInv7 = 1.0 / 7.0;
+// skimage 0.22 semantics: 7x7 uniform window (separable: axis 0 then axis 1), sample covariance (cov_norm = 49/48),
+// K1 = 0.01, K2 = 0.03, crop 3, per-plane mean.
+//
+// One block (160 threads) = a 130 x 16 tile of the cropped output = a 136 x 22 input tile.
+//   vertical pass:   thread = input column; its 22 x 2 samples come straight from global memory into registers
+//                    (a warp reads 128 contiguous bytes per row; no input staging in shared memory), running 7-row sums
+//                    of (x, y) and (x^2 + y^2, x*y) are written to shared memory as float2;
+//   horizontal pass: half-warp = strip of 13 output columns, lane & 15 = row (odd pitch: conflict-free), running
+//                    7-column sums, the SSIM map and its sum.
+// Only FOUR window sums are needed, not skimage's five: vx and vy enter S only through vx + vy.  The sums run in fp32
+// (add the entering / subtract the leaving sample, restarted every tile): skimage rounds each pass of scipy's
+// double-accumulated uniform_filter to float32; fp32 sums differ from that by a few 1e-7 per mean with random sign,
+// which moves the PLANE MEAN of S by < 1e-6 (tests hold 1e-5 against the oracle).  History: the first version kept
+// fp64 sums and scalar loads into shared memory (0.09 of the HBM peak, F2F-conversion bound); an fp32 version that
+// still staged inputs and five sums in shared memory reached 0.21, bound by ~0.9 shared-memory wavefronts per pixel;
+// this layout needs ~0.36.
+constexpr int TW = 130;                // output tile width: 130 + 120 cover the 250 output columns of a 256-wide patch
+constexpr int TH = 16;                 // output tile height = rows of one half-warp in the horizontal pass
+constexpr int NC = TW + 6;             // 136 input columns
+constexpr int NR = TH + 6;             // 22 input rows
+constexpr int PITCH = 137;             // odd: the lane-per-row walks of the horizontal pass are bank-conflict free
+constexpr int SSIM_THREADS = 160;      // >= NC; 10 half-warps x 13 output columns
+constexpr int STRIP = TW / (SSIM_THREADS / 16);   // 13
+static_assert(STRIP * (SSIM_THREADS / 16) == TW && SSIM_THREADS >= NC, "ssim tile shape");
 
-// Each pass is done in strips of 8 outputs with a running window sum (add the entering sample, subtract the
-// leaving one; all in double, where sums of seven float32 values are exact), which cuts the double adds and the
-// shared-memory reads per output by ~2.7x / 4x against recomputing every 7-tap sum.
-__global__ void __launch_bounds__(SSIM_THREADS) ssim_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                            int H, int W, float C1, float C2, float cov_norm,
-                                                            double* __restrict__ ssim_sum) {
-  __shared__ float sx[IN_T][IN_T + 1];
-  __shared__ float sy[IN_T][IN_T + 1];
-  __shared__ float v[5][TS][IN_T + 1];  // vertical (axis-0) pass of x, y, xx, yy, xy
+// Packed fp32 pairs (FADD2 / FFMA2: two IEEE fp32 operations per instruction on sm_100) carry the four window sums as
+// (sum x, sum y) and (sum x^2 + y^2, sum x*y).
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float2 moments(float2 xy) {   // (x^2 + y^2, x*y)
+  return make_float2(fmaf(xy.x, xy.x, xy.y * xy.y), xy.x * xy.y);
+}
+
+// WC: compile-time image width (0 = runtime).  With WC = 256 — the patch size of every BASELINE configuration — the
+// loads of the vertical pass are base + immediate offsets.  ncu on a 32-row-tile version (128 registers, 3 blocks =
+// 15 warps per SM): issue slots 57 % busy, DRAM 33 %, shared memory 50 % — latency bound, a block alternates between
+// waiting for its loads and computing; 16-row tiles halve the registers and the shared memory per block, so 5 blocks
+// (25 warps) overlap those phases.
+template <int WC>
+__global__ void __launch_bounds__(SSIM_THREADS, 5) ssim_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                               int H, int W_rt, float C1, float C2, float cov_norm,
+                                                               double* __restrict__ partial) {
+  const int W = WC ? WC : W_rt;
+  extern __shared__ float2 v[];         // [2][TH][PITCH]: vertical-pass 7-row SUMS of (x, y) and (x^2 + y^2, x*y)
   __shared__ double red[SSIM_THREADS / 32];
+  constexpr int Q = TH * PITCH;
 
   const int64_t plane = blockIdx.z;
   const float* pa = a + plane * static_cast<int64_t>(H) * W;
   const float* pb = b + plane * static_cast<int64_t>(H) * W;
-  const int oy0 = blockIdx.y * TS, ox0 = blockIdx.x * TS;  // origin in the cropped (H-6)x(W-6) output
-  const int OH = H - HALO, OW = W - HALO;
+  const int oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;  // origin in the cropped (H-6) x (W-6) output
+  const int OH = H - 6, OW = W - 6;
 
-  for (int i = threadIdx.x; i < IN_T * IN_T; i += SSIM_THREADS) {
-    const int r = i / IN_T, c = i - r * IN_T;
-    const int gy = oy0 + r, gx = ox0 + c;
-    const bool in = gy < H && gx < W;
-    sx[r][c] = in ? __ldg(pa + static_cast<int64_t>(gy) * W + gx) : 0.f;
-    sy[r][c] = in ? __ldg(pb + static_cast<int64_t>(gy) * W + gx) : 0.f;
-  }
-  __syncthreads();
-
-  // vertical pass: task = (column c, strip of 8 output rows)
-  for (int task = threadIdx.x; task < IN_T * (TS / 8); task += SSIM_THREADS) {
-    const int c = task % IN_T, r0 = (task / IN_T) * 8;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+  // ---- vertical pass: thread = input column, samples straight from global memory
+  {
+    const int c = threadIdx.x;
+    const int gx = ox0 + c;
+    if (c < NC) {
+      float2 xy[NR];
+      const float* qa = pa + static_cast<int64_t>(oy0) * W + gx;
+      const float* qb = pb + static_cast<int64_t>(oy0) * W + gx;
+      if (gx < W && oy0 + NR <= H) {       // interior tile: no per-sample bounds checks
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const float x = sx[r0 + k][c], y = sy[r0 + k][c];
-      s0 += static_cast<double>(x);
-      s1 += static_cast<double>(y);
-      s2 += static_cast<double>(__fmul_rn(x, x));
-      s3 += static_cast<double>(__fmul_rn(y, y));
-      s4 += static_cast<double>(__fmul_rn(x, y));
-    }
+        for (int k = 0; k < NR; ++k) xy[k] = make_float2(__ldg(qa + static_cast<int64_t>(k) * W), __ldg(qb + static_cast<int64_t>(k) * W));
+      } else {
 #pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const float x = sx[r0 + o + 6][c], y = sy[r0 + o + 6][c];
-      s0 += static_cast<double>(x);
-      s1 += static_cast<double>(y);
-      s2 += static_cast<double>(__fmul_rn(x, x));
-      s3 += static_cast<double>(__fmul_rn(y, y));
-      s4 += static_cast<double>(__fmul_rn(x, y));
-      // scipy's uniform_filter1d keeps a running mean in double and casts to float32; sum * (1/7) differs from
-      // sum / 7 by at most one double ulp, i.e. changes the float32 result in ~1e-9 of cases
-      v[0][r0 + o][c] = static_cast<float>(s0 * kInv7);
-      v[1][r0 + o][c] = static_cast<float>(s1 * kInv7);
-      v[2][r0 + o][c] = static_cast<float>(s2 * kInv7);
-      v[3][r0 + o][c] = static_cast<float>(s3 * kInv7);
-      v[4][r0 + o][c] = static_cast<float>(s4 * kInv7);
-      const float xo = sx[r0 + o][c], yo = sy[r0 + o][c];
-      s0 -= static_cast<double>(xo);
-      s1 -= static_cast<double>(yo);
-      s2 -= static_cast<double>(__fmul_rn(xo, xo));
-      s3 -= static_cast<double>(__fmul_rn(yo, yo));
-      s4 -= static_cast<double>(__fmul_rn(xo, yo));
-    }
-  }
-  __syncthreads();
-
-  // horizontal pass + SSIM map: task = (row r, strip of 8 output columns)
-  double local = 0.0;
-  for (int task = threadIdx.x; task < TS * (TS / 8); task += SSIM_THREADS) {
-    const int r = task / (TS / 8), c0 = (task % (TS / 8)) * 8;
-    if (oy0 + r >= OH) continue;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      s0 += static_cast<double>(v[0][r][c0 + k]);
-      s1 += static_cast<double>(v[1][r][c0 + k]);
-      s2 += static_cast<double>(v[2][r][c0 + k]);
-      s3 += static_cast<double>(v[3][r][c0 + k]);
-      s4 += static_cast<double>(v[4][r][c0 + k]);
-    }
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      s0 += static_cast<double>(v[0][r][c0 + o + 6]);
-      s1 += static_cast<double>(v[1][r][c0 + o + 6]);
-      s2 += static_cast<double>(v[2][r][c0 + o + 6]);
-      s3 += static_cast<double>(v[3][r][c0 + o + 6]);
-      s4 += static_cast<double>(v[4][r][c0 + o + 6]);
-      if (ox0 + c0 + o < OW) {
-        const float ux = static_cast<float>(s0 * kInv7), uy = static_cast<float>(s1 * kInv7);
-        const float uxx = static_cast<float>(s2 * kInv7), uyy = static_cast<float>(s3 * kInv7);
-        const float uxy = static_cast<float>(s4 * kInv7);
-        const float vx = __fmul_rn(cov_norm, __fsub_rn(uxx, __fmul_rn(ux, ux)));
-        const float vy = __fmul_rn(cov_norm, __fsub_rn(uyy, __fmul_rn(uy, uy)));
-        const float vxy = __fmul_rn(cov_norm, __fsub_rn(uxy, __fmul_rn(ux, uy)));
-        const float A1 = __fadd_rn(__fmul_rn(__fmul_rn(2.f, ux), uy), C1);
-        const float A2 = __fadd_rn(__fmul_rn(2.f, vxy), C2);
-        const float B1 = __fadd_rn(__fadd_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)), C1);
-        const float B2 = __fadd_rn(__fadd_rn(vx, vy), C2);
-        const float D = __fmul_rn(B1, B2);
-        const float S = __fdiv_rn(__fmul_rn(A1, A2), D);
-        local += static_cast<double>(S);
+        for (int k = 0; k < NR; ++k) {
+          const bool in = gx < W && oy0 + k < H;
+          xy[k] = in ? make_float2(__ldg(qa + static_cast<int64_t>(k) * W), __ldg(qb + static_cast<int64_t>(k) * W))
+                     : make_float2(0.f, 0.f);
+        }
       }
-      s0 -= static_cast<double>(v[0][r][c0 + o]);
-      s1 -= static_cast<double>(v[1][r][c0 + o]);
-      s2 -= static_cast<double>(v[2][r][c0 + o]);
-      s3 -= static_cast<double>(v[3][r][c0 + o]);
-      s4 -= static_cast<double>(v[4][r][c0 + o]);
+      float2 s01 = make_float2(0.f, 0.f), s23 = s01;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        s01 = add2(s01, xy[k]);
+        s23 = add2(s23, moments(xy[k]));
+      }
+#pragma unroll
+      for (int o = 0; o < TH; ++o) {
+        s01 = add2(s01, xy[o + 6]);
+        s23 = add2(s23, moments(xy[o + 6]));
+        v[o * PITCH + c] = s01;
+        v[Q + o * PITCH + c] = s23;
+        s01 = sub2(s01, xy[o]);
+        s23 = sub2(s23, moments(xy[o]));
+      }
     }
   }
-  const double t = block_sum<SSIM_THREADS>(local, red);
-  if (threadIdx.x == 0) atomicAdd(ssim_sum + plane, t);
+  __syncthreads();
+
+  // ---- horizontal pass + SSIM map: half-warp = strip of 13 output columns, lane & 15 = output row.
+  // With S0..S3 the 49-sample sums: ux = S0/49, ..., and the constants folded into the FMAs:
+  //   A1 = 2 ux uy + C1,  B1 = ux^2 + uy^2 + C1,  A2 = 2 cov (uxy - ux uy) + C2,  B2 = cov (uxx + uyy - ux^2 - uy^2) + C2
+  float local = 0.f;
+  {
+    const int r = threadIdx.x & 15, c0 = (threadIdx.x >> 4) * STRIP;
+    const int n_valid = OW - (ox0 + c0);
+    if (oy0 + r < OH && n_valid > 0) {
+      const float2* v0 = v + r * PITCH + c0;
+      float2 w01[STRIP + 6], w23[STRIP + 6];
+#pragma unroll
+      for (int k = 0; k < STRIP + 6; ++k) {
+        w01[k] = v0[k];
+        w23[k] = v0[Q + k];
+      }
+      float2 s01 = make_float2(0.f, 0.f), s23 = s01;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s01 = add2(s01, w01[k]), s23 = add2(s23, w23[k]);
+      constexpr float k1 = 1.0f / 49.0f, k2 = 1.0f / 2401.0f;
+      const float ca = 2.f * cov_norm * k1, cb = -2.f * cov_norm * k2, cc = cov_norm * k1, cd = -cov_norm * k2;
+#pragma unroll
+      for (int o = 0; o < STRIP; ++o) {
+        s01 = add2(s01, w01[o + 6]);
+        s23 = add2(s23, w23[o + 6]);
+        const float pxy = s01.x * s01.y;                       // 2401 ux uy
+        const float m2 = fmaf(s01.x, s01.x, s01.y * s01.y);    // 2401 (ux^2 + uy^2)
+        const float A1 = fmaf(pxy, 2.f * k2, C1);
+        const float B1 = fmaf(m2, k2, C1);
+        const float A2 = fmaf(s23.y, ca, fmaf(pxy, cb, C2));
+        const float B2 = fmaf(s23.x, cc, fmaf(m2, cd, C2));
+        float rden;   // B1 * B2 >= C1 * C2 > 0 and far from the denormal range: one MUFU.RCP, no range fix-up
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rden) : "f"(B1 * B2));
+        const float S = (A1 * A2) * rden;
+        local += (o < n_valid) ? S : 0.f;
+        s01 = sub2(s01, w01[o]);
+        s23 = sub2(s23, w23[o]);
+      }
+    }
+  }
+  // a thread adds at most 13 values of |S| <= 1 in fp32; everything above that is summed in fp64
+  const double t = block_sum<SSIM_THREADS>(static_cast<double>(local), red);
+  if (threadIdx.x == 0)
+    partial[(plane * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = t;
 }
+
+constexpr int SSIM_SMEM = 2 * TH * PITCH * static_cast<int>(sizeof(float2));
+SmemOptIn g_ssim_opt_in;
 
 }  // namespace
 }  // namespace b200dn
 
+extern "C" int64_t b200dn_psnr_sse_workspace_bytes(int64_t n_images, int64_t n_per_image) {
+  if (n_images <= 0 || n_per_image <= 0) return 0;
+  return n_images * b200dn::SSE_MAX_CHUNKS * static_cast<int64_t>(sizeof(double));
+}
+
+extern "C" int64_t b200dn_ssim_workspace_bytes(int64_t n_planes, int H, int W) {
+  using namespace b200dn;
+  if (n_planes <= 0 || H < 7 || W < 7) return 0;
+  return n_planes * cdiv(W - 6, TW) * cdiv(H - 6, TH) * static_cast<int64_t>(sizeof(double));
+}
+
 extern "C" int b200dn_psnr_sse(const float* a, const float* b, int64_t n_images, int64_t n_per_image, double* sse,
-                               void* stream) {
+                               void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace b200dn;
   B200DN_CHECK_ARG(a && b && sse && n_images > 0 && n_per_image > 0, "psnr_sse: bad arguments");
   B200DN_CHECK_ARG(n_images <= 65535, "psnr_sse: at most 65535 images per call");
   if (int rc = require_sm100()) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  B200DN_CUDA(cudaMemsetAsync(sse, 0, sizeof(double) * n_images, s));
   const int vec_ok = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0 && (n_per_image % 4 == 0);
   int sms = device_sm_count();
   if (sms <= 0) return B200DN_E_CUDA;
-  // enough blocks per image to cover the machine ~4x, at least 4 float4 per thread
-  int64_t chunks = cdiv64(n_per_image / 4, static_cast<int64_t>(SSE_THREADS) * 4);
-  const int64_t want = cdiv64(static_cast<int64_t>(sms) * 16, n_images);
-  if (chunks > want) chunks = want;
-  if (chunks < 1) chunks = 1;
+  const int chunks = sse_chunks(n_images, n_per_image, sms);
+  B200DN_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0 &&
+                       workspace_bytes >= n_images * chunks * static_cast<int64_t>(sizeof(double)),
+                   "psnr_sse: workspace of b200dn_psnr_sse_workspace_bytes() bytes (8-byte aligned) required");
+  double* partial = static_cast<double*>(workspace);
   dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(n_images));
-  sse_kernel<<<grid, SSE_THREADS, 0, s>>>(a, b, n_per_image, vec_ok, sse);
+  sse_kernel<<<grid, SSE_THREADS, 0, s>>>(a, b, n_per_image, vec_ok, partial);
+  B200DN_CUDA(cudaGetLastError());
+  sum_partials_kernel<<<static_cast<unsigned>(cdiv64(n_images, 4)), 128, 0, s>>>(partial, chunks, n_images, sse);
   B200DN_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int b200dn_ssim(const float* a, const float* b, int64_t n_planes, int H, int W, float data_range,
-                           double* ssim_sum, void* stream) {
+                           double* ssim_sum, void* workspace, int64_t workspace_bytes, void* stream) {
   using namespace b200dn;
   B200DN_CHECK_ARG(a && b && ssim_sum && n_planes > 0, "ssim: bad arguments");
   B200DN_CHECK_ARG(H >= 7 && W >= 7, "ssim: win_size 7 exceeds image extent %d x %d", H, W);
   B200DN_CHECK_ARG(n_planes <= 65535, "ssim: at most 65535 planes per call");
+  B200DN_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0 &&
+                       workspace_bytes >= b200dn_ssim_workspace_bytes(n_planes, H, W),
+                   "ssim: workspace of b200dn_ssim_workspace_bytes() bytes (8-byte aligned) required");
   if (int rc = require_sm100()) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  B200DN_CUDA(cudaMemsetAsync(ssim_sum, 0, sizeof(double) * n_planes, s));
+  static const void* const kernels[2] = {reinterpret_cast<const void*>(ssim_kernel<0>),
+                                         reinterpret_cast<const void*>(ssim_kernel<256>)};
+  if (int rc = ensure_max_dyn_smem(g_ssim_opt_in, kernels, 2, SSIM_SMEM, "cudaFuncSetAttribute(ssim_kernel, smem)")) return rc;
   // python: C1 = (K1*R)**2 in double, then used against float32 arrays (NEP 50 weak scalar -> float32)
   const double R = static_cast<double>(data_range);
   const float C1 = static_cast<float>((0.01 * R) * (0.01 * R));
   const float C2 = static_cast<float>((0.03 * R) * (0.03 * R));
   const float cov_norm = static_cast<float>(49.0 / 48.0);
-  dim3 grid(cdiv(W - HALO, TS), cdiv(H - HALO, TS), static_cast<unsigned>(n_planes));
-  ssim_kernel<<<grid, SSIM_THREADS, 0, s>>>(a, b, H, W, C1, C2, cov_norm, ssim_sum);
+  dim3 grid(cdiv(W - 6, TW), cdiv(H - 6, TH), static_cast<unsigned>(n_planes));
+  double* partial = static_cast<double*>(workspace);
+  if (W == 256)
+    ssim_kernel<256><<<grid, SSIM_THREADS, SSIM_SMEM, s>>>(a, b, H, W, C1, C2, cov_norm, partial);
+  else
+    ssim_kernel<0><<<grid, SSIM_THREADS, SSIM_SMEM, s>>>(a, b, H, W, C1, C2, cov_norm, partial);
+  B200DN_CUDA(cudaGetLastError());
+  sum_partials_kernel<<<static_cast<unsigned>(cdiv64(n_planes, 4)), 128, 0, s>>>(partial, grid.x * grid.y, n_planes, ssim_sum);
   B200DN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -5,6 +5,7 @@
   * ``peak_signal_noise_ratio(gt, out, data_range=...)``     skimage call at evaluate_SIDD/evaluate_SIDD.py:63
   * ``structural_similarity(gt, out, data_range=..., channel_axis=...)``   evaluate_SIDD/evaluate_SIDD.py:64
   * ``psnr_torch(pred, target)``                             diffusion_denoising/hyperparams_search.py:11-16
+  * ``welch(x, nperseg=256)``                                scipy.signal.welch call at evaluate_Unet_diffusion/plot.py:155-157
 
 The batch entry points (``batch_sse`` / ``batch_ssim`` / ``batch_metrics``) keep everything on the GPU and
 return fp64 device tensors, so a sharded evaluation can all-reduce sums without a per-image host sync
@@ -21,7 +22,7 @@ import torch
 from . import _lib
 
 __all__ = ["batch_sse", "batch_ssim_planes", "batch_metrics", "calculate_psnr", "calculate_ssim",
-           "peak_signal_noise_ratio", "structural_similarity", "psnr_torch"]
+           "peak_signal_noise_ratio", "structural_similarity", "psnr_torch", "welch", "high_frequency_psd_mae"]
 
 
 def _as_dev_f32(x, like: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -40,6 +41,12 @@ def _as_dev_f32(x, like: Optional[torch.Tensor] = None) -> torch.Tensor:
     return x.detach().to(torch.float32)
 
 
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Per-call partial-sum workspace (fp64 words) of the two-pass, fixed-order reductions.  Allocated through
+    torch's caching allocator on the current stream, so consecutive calls reuse the same block without a sync."""
+    return torch.empty(max(1, (int(nbytes) + 7) // 8), dtype=torch.float64, device=device)
+
+
 def batch_sse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """Per-image sum of squared differences; a, b: [N, ...] fp32 CUDA.  Returns fp64 [N] (device)."""
     a = _as_dev_f32(a).contiguous()
@@ -49,11 +56,13 @@ def batch_sse(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     n = a.shape[0]
     per = a.numel() // max(n, 1)
     out = torch.empty(n, dtype=torch.float64, device=a.device)
+    L = _lib.lib()
     with torch.cuda.device(a.device):
         for i0 in range(0, n, 65535):
             i1 = min(n, i0 + 65535)
-            rc = _lib.lib().b200dn_psnr_sse(a[i0:i1].data_ptr(), b[i0:i1].data_ptr(), i1 - i0, per,
-                                            out[i0:i1].data_ptr(), torch.cuda.current_stream(a.device).cuda_stream)
+            ws = _workspace(L.b200dn_psnr_sse_workspace_bytes(i1 - i0, per), a.device)
+            rc = L.b200dn_psnr_sse(a[i0:i1].data_ptr(), b[i0:i1].data_ptr(), i1 - i0, per, out[i0:i1].data_ptr(),
+                                   ws.data_ptr(), ws.numel() * 8, torch.cuda.current_stream(a.device).cuda_stream)
             _lib.check(rc, "psnr_sse")
     return out
 
@@ -68,11 +77,14 @@ def batch_ssim_planes(a: torch.Tensor, b: torch.Tensor, data_range: float) -> to
     if min(H, W) < 7:
         raise ValueError("win_size exceeds image extent.")  # skimage's message
     out = torch.empty(P, dtype=torch.float64, device=a.device)
+    L = _lib.lib()
     with torch.cuda.device(a.device):
         for i0 in range(0, P, 65535):
             i1 = min(P, i0 + 65535)
-            rc = _lib.lib().b200dn_ssim(a[i0:i1].data_ptr(), b[i0:i1].data_ptr(), i1 - i0, H, W, float(data_range),
-                                        out[i0:i1].data_ptr(), torch.cuda.current_stream(a.device).cuda_stream)
+            ws = _workspace(L.b200dn_ssim_workspace_bytes(i1 - i0, H, W), a.device)
+            rc = L.b200dn_ssim(a[i0:i1].data_ptr(), b[i0:i1].data_ptr(), i1 - i0, H, W, float(data_range),
+                               out[i0:i1].data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                               torch.cuda.current_stream(a.device).cuda_stream)
             _lib.check(rc, "ssim")
     return out / float((H - 6) * (W - 6))
 
@@ -140,3 +152,44 @@ def psnr_torch(pred: torch.Tensor, target: torch.Tensor) -> float:
     if mse == 0:
         return float("inf")
     return 20 * math.log10(1.0 / math.sqrt(mse))
+
+
+# ----------------------------------------------------------------------------- frequency-domain analysis (plot.py)
+def welch(x, nperseg: int = 256) -> Tuple[np.ndarray, torch.Tensor]:
+    """``scipy.signal.welch(x, nperseg=256)`` on the device (plot.py:155-157 calls it on ``image.flatten()``).
+
+    x: CUDA tensor (or numpy array) whose LAST axis is the signal — scipy's ``axis=-1`` — e.g. ``img.flatten()`` or a
+    batch ``imgs.flatten(1)``.  Returns ``(f, Pxx)``: ``f`` the 129 sample frequencies k/256 as a float64 numpy array
+    (as scipy returns them) and ``Pxx`` a float32 CUDA tensor ``[..., 129]``.  Only scipy's defaults at nperseg = 256
+    are implemented (fs = 1, Hann, noverlap = 128, constant detrend, one-sided density, mean)."""
+    if nperseg != 256:
+        raise NotImplementedError("only nperseg=256 (the reference's call) is implemented on device")
+    t = _as_dev_f32(x).contiguous()
+    n = t.shape[-1]
+    if n < 256:
+        raise ValueError("nperseg = 256 is greater than the input length")   # scipy warns and shrinks; not supported here
+    flat = t.reshape(-1, n)
+    S = flat.shape[0]
+    out = torch.empty((S, 129), dtype=torch.float32, device=t.device)
+    L = _lib.lib()
+    with torch.cuda.device(t.device):
+        for i0 in range(0, S, 65535):
+            i1 = min(S, i0 + 65535)
+            nbytes = L.b200dn_welch_psd_workspace_bytes(i1 - i0, n)
+            ws = torch.empty(max(1, (nbytes + 3) // 4), dtype=torch.float32, device=t.device)
+            rc = L.b200dn_welch_psd(flat[i0:i1].data_ptr(), i1 - i0, n, out[i0:i1].data_ptr(), ws.data_ptr(), ws.numel() * 4,
+                                    torch.cuda.current_stream(t.device).cuda_stream)
+            _lib.check(rc, "welch_psd")
+    f = np.arange(129, dtype=np.float64) / 256.0
+    return f, out.reshape(t.shape[:-1] + (129,))
+
+
+def high_frequency_psd_mae(gt, pred, high_freq_threshold: float = 0.5) -> torch.Tensor:
+    """``mean(|Pxx_gt[f >= thr * max f] - Pxx_pred[...]|)`` per image — the statistic plot.py:159-165 derives from the
+    three Welch calls.  gt, pred: [B, ...] CUDA batches; returns a float32 CUDA tensor [B] (no host sync)."""
+    g = _as_dev_f32(gt)
+    p = _as_dev_f32(pred, g)
+    f, pg = welch(g.flatten(1))
+    _, pp = welch(p.flatten(1))
+    idx = torch.from_numpy(np.nonzero(f >= high_freq_threshold * f.max())[0]).to(g.device)
+    return (pg.index_select(1, idx) - pp.index_select(1, idx)).abs().mean(dim=1)
