@@ -21,6 +21,8 @@
  *                           the same layers as b200dn_igemm, with the launch configuration and the encoded tensor
  *                           maps kept in an opaque handle: the ~70 modules RDUNet.forward chains per call
  *                           (UNet/RDUNet_model.py:157-186) become one C call over a prebuilt list
+ *   b200dn_dense_block_prepare / b200dn_pack_dense_block_weights
+ *                           DenoisingBlock as one kernel             UNet/RDUNet_model.py:95-115
  *   b200dn_conv_in          InputBlock.conv_1 + actv_1, t-plane cat  UNet/RDUNet_model.py:71-81,
  *                                                                    diffusion_denoising/Unet/Unet_model.py:133-136
  *   b200dn_pack_conv_weight / b200dn_pack_convt_weight
@@ -163,6 +165,33 @@ typedef struct b200dn_igemm_plan_info {
 } b200dn_igemm_plan_info;
 
 int b200dn_igemm_plan(const b200dn_igemm_args* args, int sm_count, b200dn_igemm_plan_info* info);
+
+/* ---- fused dense block --------------------------------------------------------
+ * A whole DenoisingBlock (UNet/RDUNet_model.py:95-115: four chained 3x3 conv + PReLU over the growing concatenation,
+ * then `+ x`) of the 32-channel level as ONE kernel: input-stationary passes whose partial sums stay in TMEM, o0..o2
+ * only in shared memory.  Reads channels [0, 32) of `in`, writes channels [out_coff, out_coff + 32) of `out`
+ * (NHWC 16-bit; `in` and `out` must be different buffers).  Same 16-bit rounding points as four b200dn_igemm launches.
+ * Only channels == 32 and B200DN_PREC_BF16 / B200DN_PREC_FP16 are supported (B200DN_E_ARG otherwise).
+ * The handle is launched / released with b200dn_igemm_launch[_list] / b200dn_igemm_release.                    */
+typedef struct b200dn_dense_block_args {
+  int32_t prec;
+  int32_t B, H, W;
+  int32_t channels;          /* C = 32; growth C / 2                                              */
+  const void* in;            /* NHWC 16-bit, in_ctot channels per pixel                           */
+  int32_t in_ctot;
+  void* out;
+  int32_t out_ctot, out_coff;
+  const void* wfused;        /* from b200dn_pack_dense_block_weights                              */
+  const float* bias[4];      /* conv_0..3 biases: 16, 16, 16, 32 floats                           */
+  const float* slope[4];     /* actv_0..3 PReLU slopes, same shapes                               */
+  int32_t max_ctas;          /* 0 = one per SM                                                    */
+  int32_t* sat_flag;         /* optional fp16 saturation watch (see b200dn_igemm_args)            */
+} b200dn_dense_block_args;
+/* w0..w3: conv_0..3 weights, OIHW fp32 [16,32,3,3], [16,48,3,3], [16,64,3,3], [32,80,3,3]        */
+int64_t b200dn_dense_block_weight_bytes(int channels);
+int b200dn_pack_dense_block_weights(const float* w0, const float* w1, const float* w2, const float* w3,
+                                    int channels, int prec, void* packed, void* stream);
+int b200dn_dense_block_prepare(const b200dn_dense_block_args* args, b200dn_igemm_prepared** out);
 
 /* ---- input block conv_1 (Cin = 3 or 4), CUDA cores, fp32 math ---------------
  * x: fp32 NCHW [Bx,3,H,W]; image b of the output reads x[b % Bx].

@@ -28,6 +28,7 @@ EXPORTS = (
     "b200dn_pack_conv_weight", "b200dn_pack_convt_weight", "b200dn_packed_weight_bytes",
     "b200dn_igemm", "b200dn_igemm_plan", "b200dn_igemm_prepare", "b200dn_igemm_rebind_nchw", "b200dn_igemm_launch",
     "b200dn_igemm_launch_list", "b200dn_igemm_release", "b200dn_conv_in",
+    "b200dn_dense_block_weight_bytes", "b200dn_pack_dense_block_weights", "b200dn_dense_block_prepare",
     "b200dn_sampler_step", "b200dn_lerp",
     "b200dn_psnr_sse", "b200dn_ssim", "b200dn_psnr_sse_workspace_bytes", "b200dn_ssim_workspace_bytes",
     "b200dn_welch_psd", "b200dn_welch_psd_workspace_bytes",
@@ -49,6 +50,17 @@ class IgemmArgs(C.Structure):
         ("out_nchw", C.c_void_p), ("res_nchw", C.c_void_p), ("res_bmod", C.c_int32),
         ("block_n", C.c_int32), ("max_ctas", C.c_int32), ("m_tiles", C.c_int32), ("impl", C.c_int32),
         ("sat_flag", C.c_void_p),
+    ]
+
+
+class DenseBlockArgs(C.Structure):
+    """struct b200dn_dense_block_args"""
+    _fields_ = [
+        ("prec", C.c_int32), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("channels", C.c_int32),
+        ("in_", C.c_void_p), ("in_ctot", C.c_int32),
+        ("out", C.c_void_p), ("out_ctot", C.c_int32), ("out_coff", C.c_int32),
+        ("wfused", C.c_void_p), ("bias", C.c_void_p * 4), ("slope", C.c_void_p * 4),
+        ("max_ctas", C.c_int32), ("sat_flag", C.c_void_p),
     ]
 
 
@@ -108,6 +120,10 @@ def lib() -> C.CDLL:
     L.b200dn_igemm_launch_list.argtypes = [C.POINTER(vp), i32, vp]
     L.b200dn_igemm_release.argtypes = [vp]
     L.b200dn_igemm_release.restype = None
+    L.b200dn_dense_block_weight_bytes.restype = i64
+    L.b200dn_dense_block_weight_bytes.argtypes = [i32]
+    L.b200dn_pack_dense_block_weights.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+    L.b200dn_dense_block_prepare.argtypes = [C.POINTER(DenseBlockArgs), C.POINTER(vp)]
     L.b200dn_conv_in.argtypes = [vp, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp]
     L.b200dn_sampler_step.argtypes = [vp, vp, vp, vp, f32, f32, f32, f32, vp, i64, vp]
     L.b200dn_lerp.argtypes = [vp, vp, f32, f32, vp, i64, vp]
@@ -128,7 +144,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)
         if name not in ("b200dn_last_error", "b200dn_packed_weight_bytes", "b200dn_igemm_release",
                         "b200dn_psnr_sse_workspace_bytes", "b200dn_ssim_workspace_bytes",
-                        "b200dn_welch_psd_workspace_bytes"):
+                        "b200dn_welch_psd_workspace_bytes", "b200dn_dense_block_weight_bytes"):
             fn.restype = i32
     if L.b200dn_abi_version() != ABI_VERSION:
         raise RuntimeError("libb200dn.so ABI version mismatch; rebuild the library")

@@ -1,0 +1,461 @@
+// dense_block_sm100.cu — a whole DenoisingBlock (UNet/RDUNet_model.py:95-115) of the 32-channel level in ONE kernel.
+//
+//   o0 = P(conv_0(x)); o1 = P(conv_1([x,o0])); o2 = P(conv_2([x,o0,o1])); o3 = P(conv_3([x,o0,o1,o2])); out = o3 + x
+//   (C = 32 input channels, growth g = 16; the level-0 blocks of the reference's evaluation network RDUNet_T(32),
+//   evaluate_model.py:103-105 — 8 of the 14 blocks' pixels, 38 % of the sampler's time when run layer by layer.)
+//
+// Why a fused kernel.  Layer by layer these convolutions have N = 16 / 32 output channels and every tcgen05.mma reads
+// its whole A tile (128 pixels x 16 channels = 4 KB) from shared memory whatever N is: ~32 clocks per UMMA for
+// N <= 64, so the four launches of a block cost 126 UMMAs per 128 pixels for 5.7 GFLOP of work, plus four passes
+// over a 160-byte-per-pixel NHWC buffer of which only a channel prefix is useful (ncu, profiles/r02_base_*.txt).
+// A convolution is linear in its input channels, so the block can be evaluated INPUT-stationary instead:
+//
+//   pass 0: A = x  (K = 9 x 32) -> N = 80 columns: o0 complete, partial sums of o1, o2, o3
+//   pass 1: A = o0 (K = 9 x 16) -> N = 64: o1 complete, partials of o2, o3
+//   pass 2: A = o1 (K = 9 x 16) -> N = 48: o2 complete, partial of o3
+//   pass 3: A = o2 (K = 9 x 16) -> N = 32: o3 complete
+//
+// 45 UMMAs per 128 pixels instead of 126, each activation read from shared memory once per tap instead of once per
+// tap and consumer.  The partial sums stay in TMEM (fp32) between passes; o0..o2 live only in shared memory (16-bit,
+// the same rounding as the layer-by-layer path), so HBM sees x once and the output once.  The price is the halo: a CTA
+// produces an 18 x 26 output region from a 26 x 34 input frame and recomputes o0..o2 on a border that shrinks by one
+// pixel per pass — 6 accumulator tiles (3 x 2 of 8 x 16 pixels = frame pixels [1,33) x [1,25), the same grid in every
+// pass; 80 TMEM columns each = 480 of 512), 270 UMMAs per 468 output pixels = 74 per 128.
+//
+// Shared memory (1 CTA per SM, 226 KB): X frame [34 x 26 px][32 ch] (TMA, 64-byte swizzle, OOB zero fill = conv padding),
+// O0 / O1 / O2 [frame px][16 ch] (32-byte swizzle, written by the epilogue through the generic proxy), and the block's
+// whole weight set, resident, repacked per pass as [tap][N][K] (46 + 18 + 14 + 9 KB).  Activations outside the IMAGE
+// are stored as zeros (each conv zero-pads its own input); accumulator rows outside the useful border are never stored.
+//
+// Warp roles (384 threads): hw warps 0-3 / 8-11 = two epilogue groups (tiles alternate), 4 = TMA producer,
+// 5 = MMA issuer, 6 = TMEM allocator.  The next region's X frame is loaded as soon as pass 0 has retired (the
+// residual `+ x` is re-read from global memory), so its latency hides behind passes 1-3.
+#include "igemm_common.cuh"
+
+namespace b200dn {
+namespace igemm {
+
+namespace {
+
+constexpr int DC = 32, DG = 16;             // channels, growth
+constexpr int RW = 18, RH = 26;             // output region per CTA
+constexpr int FP = RW + 8, FR = RH + 8;     // frame pitch (26 px) and rows (34)
+constexpr int NTILE = 6;                    // 3 (x) x 2 (y) accumulator tiles of 8 x 16 pixels
+constexpr int NACC = 80;                    // TMEM columns per tile: o0 | o1 | o2 | o3(32)
+constexpr int DTHREADS = 384;
+
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr uint32_t X_BYTES = FR * FP * 64;                 // 56576
+constexpr uint32_t OFF_X = 0;
+constexpr uint32_t OFF_O0 = 56832;                         // X rounded up to 512
+constexpr uint32_t OFF_O1 = OFF_O0 + 27648;                // O0: 858 px x 32 B, rounded to 256
+constexpr uint32_t OFF_O2 = OFF_O1 + 26624;                // O1: 830 px
+constexpr uint32_t OFF_W0 = OFF_O2 + 26112;                // O2: 803 px (rounded so that W0 starts on a 512-byte atom)
+constexpr uint32_t W0_BYTES = 9 * 80 * 64, W1_BYTES = 9 * 64 * 32, W2_BYTES = 9 * 48 * 32, W3_BYTES = 9 * 32 * 32;
+constexpr uint32_t OFF_W1 = OFF_W0 + W0_BYTES, OFF_W2 = OFF_W1 + W1_BYTES, OFF_W3 = OFF_W2 + W2_BYTES;
+constexpr uint32_t OFF_CTRL = OFF_W3 + W3_BYTES;           // 224512
+constexpr uint32_t CTRL_BYTES = 256;                       // mbarriers + TMEM pointer
+constexpr uint32_t OFF_BIAS = OFF_CTRL + CTRL_BYTES;       // 80 floats bias, 80 floats slope
+constexpr uint32_t DSMEM_BYTES = 1024 + OFF_BIAS + 2 * NACC * 4;
+static_assert(OFF_W0 % 512 == 0 && OFF_W1 % 256 == 0 && OFF_W2 % 256 == 0 && OFF_W3 % 256 == 0, "swizzle atoms");
+static_assert(OFF_O0 % 256 == 0 && OFF_O1 % 256 == 0 && OFF_O2 % 256 == 0, "swizzle atoms");
+static_assert(DSMEM_BYTES <= 232448, "dense block kernel exceeds 227 KB of shared memory");
+
+// barrier map (byte offsets from bars)
+constexpr uint32_t DB_W = 0, DB_XFULL = 8, DB_XEMPTY = 16, DB_TFULL = 24, DB_OREADY = 24 + 8 * NTILE, DB_TMEM = 24 + 16 * NTILE;
+
+// UMMA shared-memory descriptor, K-major, swizzle given by `layout` (2 = 128 B, 4 = 64 B, 6 = 32 B)
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void tmem_alloc_all(uint32_t dst_smem) { tmem_alloc(dst_smem, 512u); }
+
+template <bool kBf16>
+__global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_constant__ FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t sb = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (sb - raw_u32);
+  const uint32_t bars = sb + OFF_CTRL;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sg + OFF_CTRL + DB_TMEM);
+  float* s_bias = reinterpret_cast<float*>(sg + OFF_BIAS);
+  float* s_slope = s_bias + NACC;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmW[0]);
+    tma_prefetch_desc(&p.tmW[1]);
+    tma_prefetch_desc(&p.tmW[2]);
+    tma_prefetch_desc(&p.tmW[3]);
+  }
+  if (warp == 5 && lane == 0) {
+    mbar_init(bars + DB_W, 1);
+    mbar_init(bars + DB_XFULL, 1);
+    mbar_init(bars + DB_XEMPTY, 1);
+    for (int t = 0; t < NTILE; ++t) {
+      mbar_init(bars + DB_TFULL + t * 8, 1);     // one tcgen05.commit per pass
+      mbar_init(bars + DB_OREADY + t * 8, 4);    // one arrive per epilogue warp of the tile's group
+    }
+    mbar_fence_init();
+  }
+  if (warp == 6) {
+    tmem_alloc_all(smem_u32(tmem_ptr_s));
+    tmem_relinquish();
+  }
+  // bias / slopes of the four convs in accumulator-column order (static data: no dependency on the previous kernel)
+  if (threadIdx.x < NACC) {
+    const int c = threadIdx.x;
+    const int j = c < 48 ? c >> 4 : 3, k = c < 48 ? c & 15 : c - 48;
+    s_bias[c] = __ldg(p.bias[j] + k);
+    s_slope[c] = __ldg(p.slope[j] + k);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  griddep_launch_dependents();
+
+  const int num_regions = p.num_regions, grid = gridDim.x;
+  const int regions_x = p.regions_x, per_img = p.regions_x * p.regions_y;
+  const int H = p.H, W = p.W;
+
+  if (warp == 4) {
+    // ===================================================== producer: resident weights once, one X frame per region
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bars + DB_W, W0_BYTES + W1_BYTES + W2_BYTES + W3_BYTES);
+      tma_load_3d(sb + OFF_W0, &p.tmW[0], bars + DB_W, 0, 0, 0);
+      tma_load_3d(sb + OFF_W1, &p.tmW[1], bars + DB_W, 0, 0, 0);
+      tma_load_3d(sb + OFF_W2, &p.tmW[2], bars + DB_W, 0, 0, 0);
+      tma_load_3d(sb + OFF_W3, &p.tmW[3], bars + DB_W, 0, 0, 0);
+    }
+    __syncwarp();
+    griddep_wait();   // activations of the previous kernel
+    int it = 0;
+    for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
+      const int b = region / per_img, r = region - b * per_img;
+      const int ry = r / regions_x, rx = r - ry * regions_x;
+      if (it > 0) mbar_wait(bars + DB_XEMPTY, static_cast<uint32_t>((it - 1) & 1));
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bars + DB_XFULL, X_BYTES);
+        tma_load_4d(sb + OFF_X, &p.tmX, bars + DB_XFULL, 0, rx * RW - 4, ry * RH - 4, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // ===================================================== MMA issuer
+    const uint32_t fmt = static_cast<uint32_t>(p.fmt);
+    const uint32_t idesc[4] = {make_idesc_f16(fmt, 80), make_idesc_f16(fmt, 64), make_idesc_f16(fmt, 48), make_idesc_f16(fmt, 32)};
+    mbar_wait(bars + DB_W, 0);
+    int it = 0;
+    for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
+      mbar_wait(bars + DB_XFULL, static_cast<uint32_t>(it & 1));
+#pragma unroll 1
+      for (int ps = 0; ps < 4; ++ps) {
+        const uint32_t a_base = ps == 0 ? sb + OFF_X : ps == 1 ? sb + OFF_O0 : ps == 2 ? sb + OFF_O1 : sb + OFF_O2;
+        const uint32_t w_base = ps == 0 ? sb + OFF_W0 : ps == 1 ? sb + OFF_W1 : ps == 2 ? sb + OFF_W2 : sb + OFF_W3;
+        const uint32_t rowb = ps == 0 ? 64u : 32u;              // bytes per pixel row of A / per output row of B
+        const uint32_t layout = ps == 0 ? 4u : 6u;              // 64-byte / 32-byte swizzle
+        const uint32_t n_rows = ps == 0 ? 80u : ps == 1 ? 64u : ps == 2 ? 48u : 32u;
+        const uint32_t w_tap_bytes = n_rows * rowb;
+        const uint32_t id = idesc[ps];
+        const uint32_t done_par = static_cast<uint32_t>((it * 4 + ps - 1) & 1);   // completion (it*4 + ps - 1) of o_ready
+        // Each completion of an o_ready barrier is waited for ONCE: as soon as this warp has issued tile t of this
+        // pass, tile t's epilogue may complete the barrier's NEXT phase, after which a second parity wait for the
+        // old phase would never return.
+        uint32_t seen = 0;
+#pragma unroll 1
+        for (int t = 0; t < NTILE; ++t) {
+          const int tx = t >> 1, ty = t & 1;
+          // dependencies: the epilogues whose output (or TMEM columns) this tile's MMAs touch
+          if (ps == 0) {
+            if (it > 0) mbar_wait(bars + DB_OREADY + t * 8, done_par);       // previous region's last epilogue of tile t
+          } else {
+            for (int t2 = 0; t2 < NTILE; ++t2) {
+              const int dx = (t2 >> 1) - tx;
+              if (dx >= -1 && dx <= 1 && !((seen >> t2) & 1u)) {
+                mbar_wait(bars + DB_OREADY + t2 * 8, done_par);
+                seen |= 1u << t2;
+              }
+            }
+          }
+          tc_fence_after();
+          const uint32_t d = tmem_base + static_cast<uint32_t>(t * NACC + ps * 16);
+          // Every pass uses the SAME pixel <-> accumulator-row grid (frame pixels [1,33) x [1,25)): the partial sums a
+          // pass leaves in TMEM belong to the pixel the next pass adds to.  Only the useful border shrinks per pass.
+          const uint32_t o_pix = static_cast<uint32_t>((16 * ty) * FP + 8 * tx);   // source pixel of tap (0,0)
+          if (elect_one()) {
+            const uint64_t adesc0 = make_kmajor_desc(a_base + o_pix * rowb, FP * rowb, layout);
+            const uint64_t bdesc0 = make_kmajor_desc(w_base, 8u * rowb, layout);
+            uint32_t acc = ps == 0 ? 0u : 1u;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const uint64_t ad = adesc0 + static_cast<uint64_t>(((dy * FP + dx) * rowb) >> 4);
+                const uint64_t bd = bdesc0 + static_cast<uint64_t>(((dy * 3 + dx) * w_tap_bytes) >> 4);
+                umma_f16(d, ad, bd, id, acc);
+                acc = 1u;
+                if (ps == 0) umma_f16(d, ad + 2, bd + 2, id, 1u);   // second 16 channels of x
+              }
+            }
+            umma_commit(bars + DB_TFULL + t * 8);
+            if (ps == 0 && t == NTILE - 1) umma_commit(bars + DB_XEMPTY);   // X frame consumed: load the next one
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 4 || warp >= 8) {
+    // ===================================================== epilogue groups: tiles t = 2 * i + grp
+    const int grp = warp >= 8 ? 1 : 0;
+    const int we = warp & 3;
+    const int m = we * 32 + lane;             // accumulator row = pixel of the 8 x 16 tile
+    const int th = m >> 3, tw = m & 7;
+    const uint32_t lane_field = static_cast<uint32_t>(we * 32) << 16;
+    const uint16_t* in16 = static_cast<const uint16_t*>(p.in);
+    uint16_t* out16 = static_cast<uint16_t*>(p.out);
+    const int in_ctot = p.in_ctot, out_ctot = p.out_ctot, out_coff = p.out_coff;
+    uint32_t satm = 0;
+    griddep_wait();   // the residual is read from the previous kernel's output
+    int it = 0;
+    for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
+      const int b = region / per_img, r = region - b * per_img;
+      const int ry = r / regions_x, rx = r - ry * regions_x;
+      const int gy0 = ry * RH - 4, gx0 = rx * RW - 4;       // global coordinates of frame pixel (0, 0)
+#pragma unroll 1
+      for (int ps = 0; ps < 4; ++ps) {
+        const uint32_t par = static_cast<uint32_t>((it * 4 + ps) & 1);
+#pragma unroll 1
+        for (int i = 0; i < NTILE / 2; ++i) {
+          const int t = 2 * i + grp;
+          const int tx = t >> 1, ty = t & 1;
+          const int fy = 1 + 16 * ty + th, fx = 1 + 8 * tx + tw;               // frame pixel of this row (all passes)
+          const int gy = gy0 + fy, gx = gx0 + fx;
+          const bool in_img = gy >= 0 && gy < H && gx >= 0 && gx < W;
+          const uint32_t tcol = tmem_base + lane_field + static_cast<uint32_t>(t * NACC);
+          if (ps < 3) {
+            // ---- o_ps: bias + PReLU -> 16-bit -> shared memory (32-byte swizzled rows), zeros outside the image
+            mbar_wait(bars + DB_TFULL + t * 8, par);
+            tc_fence_after();
+            uint32_t rr[16];
+            tmem_ld16(tcol + static_cast<uint32_t>(ps * 16), rr);
+            tmem_ld_wait();
+            const bool useful = fy >= 1 + ps && fy < FR - 1 - ps && fx >= 1 + ps && fx < FP - 1 - ps;
+            if (useful) {
+              const float* bs = s_bias + ps * 16;
+              const float* ss = s_slope + ps * 16;
+              uint32_t h[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float a0 = __uint_as_float(rr[2 * j]) + bs[2 * j];
+                float a1 = __uint_as_float(rr[2 * j + 1]) + bs[2 * j + 1];
+                a0 = a0 > 0.f ? a0 : a0 * ss[2 * j];
+                a1 = a1 > 0.f ? a1 : a1 * ss[2 * j + 1];
+                h[j] = in_img ? pack2<kBf16>(a0, a1) : 0u;
+              }
+              if (!kBf16 && p.sat_flag != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
+              }
+              const uint32_t idx = static_cast<uint32_t>(fy * FP + fx);
+              const uint32_t off = (ps == 0 ? OFF_O0 : ps == 1 ? OFF_O1 : OFF_O2) + idx * 32u;
+              const uint32_t sw = ((off >> 7) & 1u) << 4;      // 32-byte swizzle: bit 4 ^= bit 7
+              *reinterpret_cast<uint4*>(sg + (off ^ sw)) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(sg + ((off + 16u) ^ sw)) = make_uint4(h[4], h[5], h[6], h[7]);
+            }
+            fence_proxy_async_smem();     // generic-proxy stores -> visible to the UMMAs of the next pass
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + DB_OREADY + t * 8);
+          } else {
+            // ---- o3 + x -> global (NHWC 16-bit channel slice), region interior only
+            const bool store = in_img && fy >= 4 && fy < 4 + RH && fx >= 4 && fx < 4 + RW;
+            const int64_t pix = (static_cast<int64_t>(b) * H + gy) * W + gx;
+            uint4 xr[4];
+            if (store) {
+              const uint4* src = reinterpret_cast<const uint4*>(in16 + pix * in_ctot);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) xr[q] = __ldg(src + q);
+            }
+            mbar_wait(bars + DB_TFULL + t * 8, par);
+            tc_fence_after();
+            uint32_t r0[16], r1[16];
+            tmem_ld16(tcol + 48u, r0);
+            tmem_ld16(tcol + 64u, r1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + DB_OREADY + t * 8);     // TMEM columns of tile t are free again
+            if (store) {
+              const float* bs = s_bias + 48;
+              const float* ss = s_slope + 48;
+              const uint32_t* xw = reinterpret_cast<const uint32_t*>(xr);
+              uint32_t h[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t ra = j < 8 ? r0[2 * j] : r1[2 * j - 16];
+                const uint32_t rb = j < 8 ? r0[2 * j + 1] : r1[2 * j - 15];
+                float a0 = __uint_as_float(ra) + bs[2 * j];
+                float a1 = __uint_as_float(rb) + bs[2 * j + 1];
+                a0 = a0 > 0.f ? a0 : a0 * ss[2 * j];
+                a1 = a1 > 0.f ? a1 : a1 * ss[2 * j + 1];
+                a0 += cvt_lo<kBf16>(xw[j]);
+                a1 += cvt_hi<kBf16>(xw[j]);
+                h[j] = pack2<kBf16>(a0, a1);
+              }
+              if (!kBf16 && p.sat_flag != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) satm = sat_track(satm, h[j]);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(out16 + pix * out_ctot + out_coff);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dst[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+            }
+          }
+        }
+      }
+    }
+    if (!kBf16) sat_report(p.sat_flag, satm);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 6) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// [pass][tap][n][k] 16-bit from the four OIHW fp32 conv weights of a block
+__global__ void pack_dense_block_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                        const float* __restrict__ w2, const float* __restrict__ w3, int is_bf16,
+                                        uint16_t* __restrict__ dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int n0 = 9 * 80 * 32, n1 = 9 * 64 * 16, n2 = 9 * 48 * 16, n3 = 9 * 32 * 16;
+  if (idx >= n0 + n1 + n2 + n3) return;
+  int ps, rem = idx;
+  if (rem < n0) ps = 0;
+  else if ((rem -= n0) < n1) ps = 1;
+  else if ((rem -= n1) < n2) ps = 2;
+  else { rem -= n2; ps = 3; }
+  const int K = ps == 0 ? 32 : 16, N = ps == 0 ? 80 : ps == 1 ? 64 : ps == 2 ? 48 : 32;
+  const int k = rem % K, n = (rem / K) % N, tap = rem / (K * N);
+  const int ci = (ps == 0 ? 0 : 16 + 16 * ps) + k;          // input channel: x 0..31, o0 32..47, o1 48..63, o2 64..79
+  // accumulator column n of pass ps -> (conv j, output channel o): columns are [conv_ps | conv_ps+1 | ... | conv_3]
+  int j = ps + (n >> 4), o = n & 15;
+  if (j >= 3) { j = 3; o = n - (3 - ps) * 16; }
+  const float* w = j == 0 ? w0 : j == 1 ? w1 : j == 2 ? w2 : w3;
+  const int cin_j = 32 + 16 * j;
+  const float v = w[(static_cast<int64_t>(o) * cin_j + ci) * 9 + tap];
+  dst[idx] = is_bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+}
+
+SmemOptIn g_dense_opt_in;
+
+}  // namespace
+
+int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_encodeTiled encode_fn) {
+  B200DN_CHECK_ARG(a.channels == DC, "dense_block: only %d-channel blocks (growth %d) are fused; got %d", DC, DG, a.channels);
+  B200DN_CHECK_ARG(a.prec == B200DN_PREC_BF16 || a.prec == B200DN_PREC_FP16, "dense_block: single-plane bf16 / fp16 only");
+  B200DN_CHECK_ARG(a.B > 0 && a.H > 0 && a.W > 0, "dense_block: non-positive dims");
+  B200DN_CHECK_ARG(a.in && a.out && a.wfused, "dense_block: null pointer");
+  for (int j = 0; j < 4; ++j) B200DN_CHECK_ARG(a.bias[j] && a.slope[j], "dense_block: null bias / slope %d", j);
+  B200DN_CHECK_ARG(a.in_ctot % 8 == 0 && a.in_ctot >= DC, "dense_block: bad in_ctot %d", a.in_ctot);
+  B200DN_CHECK_ARG(a.out_ctot % 8 == 0 && a.out_coff % 8 == 0 && a.out_coff + DC <= a.out_ctot,
+                   "dense_block: output slice [%d,%d) of %d must be 8-channel aligned", a.out_coff, a.out_coff + DC, a.out_ctot);
+  B200DN_CHECK_ARG((reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a.wfused) & 15) == 0, "dense_block: pointers must be 16-byte aligned");
+  // the residual is read from `in` while other CTAs may still need their halo of it: in-place blocks are not supported
+  B200DN_CHECK_ARG(a.in != a.out || a.out_coff >= DC, "dense_block: output slice overlaps the block input");
+  if (int rc = require_sm100()) return rc;
+  FusedParams& f = cfg->f;
+  memset(&f, 0, sizeof(f));
+  f.B = a.B, f.H = a.H, f.W = a.W;
+  f.regions_x = cdiv(a.W, RW), f.regions_y = cdiv(a.H, RH);
+  f.num_regions = a.B * f.regions_x * f.regions_y;
+  f.fmt = a.prec == B200DN_PREC_FP16 ? 0 : 1;
+  for (int j = 0; j < 4; ++j) f.bias[j] = a.bias[j], f.slope[j] = a.slope[j];
+  f.in = a.in, f.in_ctot = a.in_ctot, f.out = a.out, f.out_ctot = a.out_ctot, f.out_coff = a.out_coff;
+  f.sat_flag = a.sat_flag;
+  const CUtensorMapDataType dt = f.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  uint32_t estr[5] = {1, 1, 1, 1, 1};
+  {
+    const uint64_t ct = static_cast<uint64_t>(a.in_ctot);
+    uint64_t dims[4] = {DC, static_cast<uint64_t>(a.W), static_cast<uint64_t>(a.H), static_cast<uint64_t>(a.B)};
+    uint64_t str[3] = {ct * 2, static_cast<uint64_t>(a.W) * ct * 2, static_cast<uint64_t>(a.H) * a.W * ct * 2};
+    uint32_t box[4] = {DC, FP, FR, 1};
+    CUresult r = encode_fn(&f.tmX, dt, 4, const_cast<void*>(a.in), dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("dense_block: cuTensorMapEncodeTiled(X) failed with CUresult %d", static_cast<int>(r));
+      return B200DN_E_CUDA;
+    }
+  }
+  const uint8_t* wb = static_cast<const uint8_t*>(a.wfused);
+  const uint32_t kdim[4] = {32, 16, 16, 16}, ndim[4] = {80, 64, 48, 32};
+  uint64_t woff = 0;
+  for (int ps = 0; ps < 4; ++ps) {
+    uint64_t dims[3] = {kdim[ps], ndim[ps], 9};
+    uint64_t str[2] = {kdim[ps] * 2ull, static_cast<uint64_t>(kdim[ps]) * ndim[ps] * 2ull};
+    uint32_t box[3] = {kdim[ps], ndim[ps], 9};
+    CUresult r = encode_fn(&f.tmW[ps], dt, 3, const_cast<uint8_t*>(wb + woff), dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           ps == 0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("dense_block: cuTensorMapEncodeTiled(W%d) failed with CUresult %d", ps, static_cast<int>(r));
+      return B200DN_E_CUDA;
+    }
+    woff += static_cast<uint64_t>(kdim[ps]) * ndim[ps] * 9 * 2;
+  }
+  static const void* const kernels[2] = {reinterpret_cast<const void*>(dense_block_kernel<false>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<true>)};
+  if (int rc = ensure_max_dyn_smem(g_dense_opt_in, kernels, 2, DSMEM_BYTES, "cudaFuncSetAttribute(dense_block_kernel, smem)"))
+    return rc;
+  int sms = device_sm_count();
+  if (sms <= 0) return B200DN_E_CUDA;
+  int grid = f.num_regions < sms ? f.num_regions : sms;
+  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
+  cfg->kind = 1;
+  cfg->kernel = kernels[f.fmt];
+  cfg->grid = grid;
+  cfg->threads = DTHREADS;
+  cfg->smem = DSMEM_BYTES;
+  cfg->cluster = 1;
+  return 0;
+}
+
+int pack_dense_block(const float* w0, const float* w1, const float* w2, const float* w3, int prec, void* packed, cudaStream_t s) {
+  B200DN_CHECK_ARG(w0 && w1 && w2 && w3 && packed, "pack_dense_block: null pointer");
+  B200DN_CHECK_ARG(prec == B200DN_PREC_BF16 || prec == B200DN_PREC_FP16, "pack_dense_block: single-plane bf16 / fp16 only");
+  const int n = 9 * (80 * 32 + 64 * 16 + 48 * 16 + 32 * 16);
+  pack_dense_block_kernel<<<cdiv(n, 256), 256, 0, s>>>(w0, w1, w2, w3, prec == B200DN_PREC_BF16 ? 1 : 0,
+                                                       static_cast<uint16_t*>(packed));
+  B200DN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace igemm
+}  // namespace b200dn
+
+extern "C" int64_t b200dn_dense_block_weight_bytes(int channels) {
+  if (channels != b200dn::igemm::DC) return B200DN_E_UNSUP;
+  return 9 * (80 * 32 + 64 * 16 + 48 * 16 + 32 * 16) * 2;
+}
+
+extern "C" int b200dn_pack_dense_block_weights(const float* w0, const float* w1, const float* w2, const float* w3,
+                                               int channels, int prec, void* packed, void* stream) {
+  if (channels != b200dn::igemm::DC) {
+    b200dn::set_error("pack_dense_block_weights: only 32-channel blocks are fused (got %d)", channels);
+    return B200DN_E_UNSUP;
+  }
+  return b200dn::igemm::pack_dense_block(w0, w1, w2, w3, prec, packed, static_cast<cudaStream_t>(stream));
+}

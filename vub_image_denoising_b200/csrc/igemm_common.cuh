@@ -5,6 +5,8 @@
 #pragma once
 #include "common.cuh"
 
+#include <cudaTypedefs.h>
+
 namespace b200dn {
 namespace igemm {
 
@@ -476,13 +478,36 @@ __device__ __forceinline__ void issue_slab_block_resident(uint32_t d, uint64_t a
   }
 }
 
+// parameter block of the fused dense-block kernel (dense_block_sm100.cu)
+struct __align__(64) FusedParams {
+  CUtensorMap tmX;
+  CUtensorMap tmW[4];
+  int B, H, W;
+  int regions_x, regions_y, num_regions;
+  int fmt;                       // 1 bf16, 0 fp16
+  const float* bias[4];
+  const float* slope[4];
+  const void* in;                // block input (NHWC 16-bit, channels [0, 32)): TMA source and the `+ x` residual
+  int in_ctot;
+  void* out;
+  int out_ctot, out_coff;
+  int* sat_flag;
+};
+
 // A fully resolved launch: kernel variant, launch geometry and the parameter block (with its encoded tensor maps).
 // b200dn_igemm builds one per call; b200dn_igemm_prepare keeps it, so that later launches cost one cudaLaunchKernelExC.
 struct LaunchCfg {
-  KParams p;
+  KParams p;          // kind 0: the per-layer implicit-GEMM kernels
+  FusedParams f;      // kind 1: the fused dense block
+  int kind;
   const void* kernel;
   int grid, threads, smem, cluster;
 };
+using PFN_encodeTiled = PFN_cuTensorMapEncodeTiled;
+// the driver's cuTensorMapEncodeTiled entry point (igemm_sm100.cu); 0 on success
+int get_tensor_map_encoder(PFN_encodeTiled* fn);
+// fused dense block (dense_block_sm100.cu): validate, encode, resolve
+int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_encodeTiled encode_fn);
 // slab-kernel resolver (conv3x3_slab_sm100.cu); cfg->p is fully populated by igemm_configure.  Picks the template
 // variant and opts it in to its dynamic shared memory on the current device.
 int resolve_conv3x3_slab(LaunchCfg* cfg, int grid);

@@ -22,7 +22,6 @@
 //                     NHWC channel slice, or fp32 NCHW (+fp32 NCHW residual) for the output block.
 #include "igemm_common.cuh"
 
-#include <cudaTypedefs.h>
 #include <mutex>
 #include <new>
 #include <stdlib.h>
@@ -674,6 +673,7 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
     if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
   }
 
+  cfg->kind = 0;
   if (slab && p.cta2) return resolve_conv3x3_slab2(cfg, 2 * clusters);
   if (slab) return resolve_conv3x3_slab(cfg, grid);
 
@@ -694,10 +694,19 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
 
 int igemm_launch_cfg(const LaunchCfg& cfg, cudaStream_t stream) {
   // the parameter block is copied by the launch itself; nothing is re-encoded here
-  B200DN_CUDA(launch_pdl(cfg.kernel, cfg.grid, cfg.threads, static_cast<size_t>(cfg.smem), stream,
-                         const_cast<KParams*>(&cfg.p), cfg.cluster));
+  void* params = cfg.kind == 1 ? static_cast<void*>(const_cast<FusedParams*>(&cfg.f))
+                               : static_cast<void*>(const_cast<KParams*>(&cfg.p));
+  B200DN_CUDA(launch_pdl(cfg.kernel, cfg.grid, cfg.threads, static_cast<size_t>(cfg.smem), stream, params, cfg.cluster));
   return 0;
 }
+
+namespace igemm {
+int get_tensor_map_encoder(PFN_encodeTiled* fn) {
+  if (int rc = get_encoder()) return rc;
+  *fn = g_encode;
+  return 0;
+}
+}  // namespace igemm
 
 }  // namespace b200dn
 
@@ -741,6 +750,31 @@ extern "C" int b200dn_igemm_prepare(const b200dn_igemm_args* args, b200dn_igemm_
     return rc;
   }
   h->out_kind = args->out_kind;
+  *out = h;
+  return 0;
+}
+
+extern "C" int b200dn_dense_block_prepare(const b200dn_dense_block_args* args, b200dn_igemm_prepared** out) {
+  if (!args || !out) {
+    b200dn::set_error("dense_block_prepare: null args / out");
+    return B200DN_E_ARG;
+  }
+  *out = nullptr;
+  b200dn::igemm::PFN_encodeTiled enc = nullptr;
+  if (args->channels == 32 && (args->prec == B200DN_PREC_BF16 || args->prec == B200DN_PREC_FP16) && args->in && args->out) {
+    if (int rc = b200dn::require_sm100()) return rc;
+    if (int rc = b200dn::igemm::get_tensor_map_encoder(&enc)) return rc;
+  }
+  b200dn_igemm_prepared* h = new (std::nothrow) b200dn_igemm_prepared;
+  if (!h) {
+    b200dn::set_error("dense_block_prepare: out of host memory");
+    return B200DN_E_ARG;
+  }
+  if (int rc = b200dn::igemm::configure_dense_block(*args, &h->cfg, enc)) {
+    delete h;
+    return rc;
+  }
+  h->out_kind = B200DN_OUT_NHWC16;
   *out = h;
   return 0;
 }
