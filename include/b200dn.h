@@ -186,6 +186,7 @@ typedef struct b200dn_dense_block_args {
   const float* slope[4];     /* actv_0..3 PReLU slopes, same shapes                               */
   int32_t max_ctas;          /* 0 = one per SM                                                    */
   int32_t* sat_flag;         /* optional fp16 saturation watch (see b200dn_igemm_args)            */
+  int64_t* timeline;         /* optional diagnostics: CTA 0 writes up to 4096 (event, clock) pairs, entry 0 = count */
 } b200dn_dense_block_args;
 /* w0..w3: conv_0..3 weights, OIHW fp32 [16,32,3,3], [16,48,3,3], [16,64,3,3], [32,80,3,3]        */
 int64_t b200dn_dense_block_weight_bytes(int channels);

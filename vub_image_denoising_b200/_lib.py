@@ -60,7 +60,7 @@ class DenseBlockArgs(C.Structure):
         ("in_", C.c_void_p), ("in_ctot", C.c_int32),
         ("out", C.c_void_p), ("out_ctot", C.c_int32), ("out_coff", C.c_int32),
         ("wfused", C.c_void_p), ("bias", C.c_void_p * 4), ("slope", C.c_void_p * 4),
-        ("max_ctas", C.c_int32), ("sat_flag", C.c_void_p),
+        ("max_ctas", C.c_int32), ("sat_flag", C.c_void_p), ("timeline", C.c_void_p),
     ]
 
 

@@ -27,8 +27,8 @@
 // whole weight set, resident, repacked per pass as [tap][N][K] (46 + 18 + 14 + 9 KB).  Activations outside the IMAGE
 // are stored as zeros (each conv zero-pads its own input); accumulator rows outside the useful border are never stored.
 //
-// Warp roles (384 threads): hw warps 0-3 / 8-11 = two epilogue groups (tiles alternate), 4 = TMA producer,
-// 5 = MMA issuer, 6 = TMEM allocator.  The next region's X frame is loaded as soon as pass 0 has retired (the
+// Warp roles (512 threads): hw warps 0-11 = three epilogue groups (one per tile column, both tile rows together),
+// 12 = TMA producer, 13 / 14 = MMA issuers (one per tile row), 15 = TMEM allocator.  The next region's X frame is loaded as soon as pass 0 has retired (the
 // residual `+ x` is re-read from global memory), so its latency hides behind passes 1-3.
 #include "igemm_common.cuh"
 
@@ -42,7 +42,10 @@ constexpr int RW = 18, RH = 26;             // output region per CTA
 constexpr int FP = RW + 8, FR = RH + 8;     // frame pitch (26 px) and rows (34)
 constexpr int NTILE = 6;                    // 3 (x) x 2 (y) accumulator tiles of 8 x 16 pixels
 constexpr int NACC = 80;                    // TMEM columns per tile: o0 | o1 | o2 | o3(32)
-constexpr int DTHREADS = 384;
+constexpr int DTHREADS = 512;
+// warp roles: 0-11 epilogue (three groups of four = one per tile column), 12 TMA producer, 13 / 14 MMA issuers (one per
+// tile row), 15 TMEM allocator
+constexpr int W_PRODUCER = 12, W_ISSUER0 = 13, W_ALLOC = 15;
 
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr uint32_t X_BYTES = FR * FP * 64;                 // 56576
@@ -62,7 +65,8 @@ static_assert(OFF_O0 % 256 == 0 && OFF_O1 % 256 == 0 && OFF_O2 % 256 == 0, "swiz
 static_assert(DSMEM_BYTES <= 232448, "dense block kernel exceeds 227 KB of shared memory");
 
 // barrier map (byte offsets from bars)
-constexpr uint32_t DB_W = 0, DB_XFULL = 8, DB_XEMPTY = 16, DB_TFULL = 24, DB_OREADY = 24 + 8 * NTILE, DB_TMEM = 24 + 16 * NTILE;
+// o_ready is kept per tile COLUMN (two tiles, eight epilogue warps): a tile of the next pass needs the columns tx-1..tx+1
+constexpr uint32_t DB_W = 0, DB_XFULL = 8, DB_XEMPTY = 16, DB_TFULL = 24, DB_OCOL = 24 + 8 * NTILE, DB_TMEM = DB_OCOL + 8 * 3;
 
 // UMMA shared-memory descriptor, K-major, swizzle given by `layout` (2 = 128 B, 4 = 64 B, 6 = 32 B)
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout) {
@@ -77,6 +81,122 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
 
 __device__ __forceinline__ void tmem_alloc_all(uint32_t dst_smem) { tmem_alloc(dst_smem, 512u); }
 
+// timeline diagnostics: lane 0 of the issuer and of the first warp of each epilogue group of CTA 0 appends
+// (event id, clock) pairs to ITS OWN third of a global buffer with plain stores (no atomics: a logged event costs a
+// clock read and two fire-and-forget stores).  Layout: role r in {1,2,3} owns entries [(r-1)*1365, r*1365); slot 0 of
+// each third holds the count.
+struct DbgLog {
+  long long* base;
+  int n;
+  __device__ __forceinline__ void init(long long* dbg, int role, bool active) {
+    base = (dbg != nullptr && active && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? dbg + (role - 1) * 2730 : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void log(int ev) {
+    if (base != nullptr && n < 1360) {
+      base[2 + 2 * n] = ev;
+      base[3 + 2 * n] = clock64();
+      ++n;
+      base[0] = n;
+    }
+  }
+};
+// event ids: role * 100000 + region_local * 1000 + pass * 100 + tile * 10 + kind
+#define DBG_EV(role, it, ps, t, kind) ((role) * 100000 + (it) * 1000 + (ps) * 100 + (t) * 10 + (kind))
+
+// One pass of one tile row: for each of the three tiles, wait for the epilogues its MMAs depend on, then issue the nine
+// taps (x 2 k16 steps in pass 0) with compile-time descriptor offsets and commit to the tile's t_full barrier.
+// Every pass uses the SAME pixel <-> accumulator-row grid (frame pixels [1,33) x [1,25)): the partial sums a pass leaves
+// in TMEM belong to the pixel the next pass adds to; only the useful border shrinks per pass.
+template <int PS>
+__device__ __forceinline__ void issue_pass(uint32_t sb, uint32_t bars, uint32_t tmem_base, uint32_t fmt, int ty, int it,
+                                           DbgLog& dl) {
+  constexpr uint32_t rowb = PS == 0 ? 64u : 32u;              // bytes per pixel row of A / per output row of B
+  constexpr uint32_t layout = PS == 0 ? 4u : 6u;              // 64-byte / 32-byte swizzle
+  constexpr uint32_t n_rows = PS == 0 ? 80u : PS == 1 ? 64u : PS == 2 ? 48u : 32u;
+  constexpr uint32_t a_off = PS == 0 ? OFF_X : PS == 1 ? OFF_O0 : PS == 2 ? OFF_O1 : OFF_O2;
+  constexpr uint32_t w_off = PS == 0 ? OFF_W0 : PS == 1 ? OFF_W1 : PS == 2 ? OFF_W2 : OFF_W3;
+  const uint32_t idesc = make_idesc_f16(fmt, n_rows);
+  // completion (it * 4 + PS - 1) of the column barriers; each completion is waited for ONCE per pass: once a tile of
+  // this pass is issued its epilogue may complete the barrier's next phase, and a second wait on the old parity
+  // would never return
+  const uint32_t done_par = static_cast<uint32_t>((it * 4 + PS - 1) & 1);
+  uint32_t seen = 0;
+  const uint64_t bdesc0 = make_kmajor_desc(sb + w_off, 8u * rowb, layout);
+#pragma unroll 1
+  for (int tx = 0; tx < 3; ++tx) {
+    if (PS > 0 || it > 0) {
+      const int c_lo = PS == 0 ? tx : (tx > 0 ? tx - 1 : 0), c_hi = PS == 0 ? tx : (tx < 2 ? tx + 1 : 2);
+      for (int c = c_lo; c <= c_hi; ++c) {
+        if (!((seen >> c) & 1u)) {
+          mbar_wait(bars + DB_OCOL + c * 8, done_par);
+          seen |= 1u << c;
+        }
+      }
+    }
+    tc_fence_after();
+    const int t = 2 * tx + ty;
+    dl.log(DBG_EV(1, it, PS, t, 0));      // dependencies satisfied
+    if (elect_one()) {
+      const uint32_t d = tmem_base + static_cast<uint32_t>(t * NACC + PS * 16);
+      const uint32_t o_pix = static_cast<uint32_t>((16 * ty) * FP + 8 * tx);   // source pixel of tap (0,0)
+      const uint64_t adesc0 = make_kmajor_desc(sb + a_off + o_pix * rowb, FP * rowb, layout);
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint64_t ad = adesc0 + static_cast<uint64_t>(((dy * FP + dx) * rowb) >> 4);
+          const uint64_t bd = bdesc0 + static_cast<uint64_t>(((dy * 3 + dx) * n_rows * rowb) >> 4);
+          umma_f16(d, ad, bd, idesc, (PS == 0 && dy == 0 && dx == 0) ? 0u : 1u);
+          if (PS == 0) umma_f16(d, ad + 2, bd + 2, idesc, 1u);   // second 16 channels of x
+        }
+      }
+      umma_commit(bars + DB_TFULL + t * 8);
+    }
+    __syncwarp();
+    dl.log(DBG_EV(1, it, PS, t, 1));      // issued + committed
+  }
+}
+
+// bias + PReLU on 16 accumulator columns -> 8 packed 16-bit pairs
+template <bool kBf16>
+__device__ __forceinline__ void bias_prelu_pack16(const uint32_t (&rr)[16], const float* bs, const float* ss, uint32_t (&h)[8]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bs);
+  const float4* s4 = reinterpret_cast<const float4*>(ss);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 bb = b4[q], sl = s4[q];
+    float a0 = __uint_as_float(rr[4 * q]) + bb.x, a1 = __uint_as_float(rr[4 * q + 1]) + bb.y;
+    float a2 = __uint_as_float(rr[4 * q + 2]) + bb.z, a3 = __uint_as_float(rr[4 * q + 3]) + bb.w;
+    a0 = a0 > 0.f ? a0 : a0 * sl.x;
+    a1 = a1 > 0.f ? a1 : a1 * sl.y;
+    a2 = a2 > 0.f ? a2 : a2 * sl.z;
+    a3 = a3 > 0.f ? a3 : a3 * sl.w;
+    h[2 * q] = pack2<kBf16>(a0, a1);
+    h[2 * q + 1] = pack2<kBf16>(a2, a3);
+  }
+}
+// the same with the 16-bit residual x (8 packed pairs) added after the activation (`out_3 + x`, RDUNet_model.py:115)
+template <bool kBf16>
+__device__ __forceinline__ void bias_prelu_res_pack16(const uint32_t (&rr)[16], const float* bs, const float* ss,
+                                                      const uint4& x0, const uint4& x1, uint32_t (&h)[8]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bs);
+  const float4* s4 = reinterpret_cast<const float4*>(ss);
+  const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 bb = b4[q], sl = s4[q];
+    float a0 = __uint_as_float(rr[4 * q]) + bb.x, a1 = __uint_as_float(rr[4 * q + 1]) + bb.y;
+    float a2 = __uint_as_float(rr[4 * q + 2]) + bb.z, a3 = __uint_as_float(rr[4 * q + 3]) + bb.w;
+    a0 = (a0 > 0.f ? a0 : a0 * sl.x) + cvt_lo<kBf16>(xw[2 * q]);
+    a1 = (a1 > 0.f ? a1 : a1 * sl.y) + cvt_hi<kBf16>(xw[2 * q]);
+    a2 = (a2 > 0.f ? a2 : a2 * sl.z) + cvt_lo<kBf16>(xw[2 * q + 1]);
+    a3 = (a3 > 0.f ? a3 : a3 * sl.w) + cvt_hi<kBf16>(xw[2 * q + 1]);
+    h[2 * q] = pack2<kBf16>(a0, a1);
+    h[2 * q + 1] = pack2<kBf16>(a2, a3);
+  }
+}
+
 template <bool kBf16>
 __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -90,24 +210,22 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == W_PRODUCER && lane == 0) {
     tma_prefetch_desc(&p.tmX);
     tma_prefetch_desc(&p.tmW[0]);
     tma_prefetch_desc(&p.tmW[1]);
     tma_prefetch_desc(&p.tmW[2]);
     tma_prefetch_desc(&p.tmW[3]);
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == W_ISSUER0 && lane == 0) {
     mbar_init(bars + DB_W, 1);
     mbar_init(bars + DB_XFULL, 1);
-    mbar_init(bars + DB_XEMPTY, 1);
-    for (int t = 0; t < NTILE; ++t) {
-      mbar_init(bars + DB_TFULL + t * 8, 1);     // one tcgen05.commit per pass
-      mbar_init(bars + DB_OREADY + t * 8, 4);    // one arrive per epilogue warp of the tile's group
-    }
+    mbar_init(bars + DB_XEMPTY, 2);              // one tcgen05.commit per issuer warp
+    for (int t = 0; t < NTILE; ++t) mbar_init(bars + DB_TFULL + t * 8, 1);     // one tcgen05.commit per pass
+    for (int c = 0; c < 3; ++c) mbar_init(bars + DB_OCOL + c * 8, 4);          // one arrive per warp of the column's group
     mbar_fence_init();
   }
-  if (warp == 6) {
+  if (warp == W_ALLOC) {
     tmem_alloc_all(smem_u32(tmem_ptr_s));
     tmem_relinquish();
   }
@@ -128,7 +246,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
   const int regions_x = p.regions_x, per_img = p.regions_x * p.regions_y;
   const int H = p.H, W = p.W;
 
-  if (warp == 4) {
+  if (warp == W_PRODUCER) {
     // ===================================================== producer: resident weights once, one X frame per region
     if (elect_one()) {
       mbar_arrive_expect_tx(bars + DB_W, W0_BYTES + W1_BYTES + W2_BYTES + W3_BYTES);
@@ -150,178 +268,153 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
       }
       __syncwarp();
     }
-  } else if (warp == 5) {
-    // ===================================================== MMA issuer
+  } else if (warp == W_ISSUER0 || warp == W_ISSUER0 + 1) {
+    // ===================================================== MMA issuers: one warp per tile row
+    // (a single issuing thread needs ~100 clocks per UMMA for descriptor arithmetic on the uniform datapath — the
+    // timeline of the first version showed the tensor pipe idle behind it; two issuers and compile-time tap offsets)
+    const int ty = warp - W_ISSUER0;
     const uint32_t fmt = static_cast<uint32_t>(p.fmt);
-    const uint32_t idesc[4] = {make_idesc_f16(fmt, 80), make_idesc_f16(fmt, 64), make_idesc_f16(fmt, 48), make_idesc_f16(fmt, 32)};
+    DbgLog dl;
+    dl.init(p.dbg, 1, ty == 0);
     mbar_wait(bars + DB_W, 0);
     int it = 0;
     for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
       mbar_wait(bars + DB_XFULL, static_cast<uint32_t>(it & 1));
-#pragma unroll 1
-      for (int ps = 0; ps < 4; ++ps) {
-        const uint32_t a_base = ps == 0 ? sb + OFF_X : ps == 1 ? sb + OFF_O0 : ps == 2 ? sb + OFF_O1 : sb + OFF_O2;
-        const uint32_t w_base = ps == 0 ? sb + OFF_W0 : ps == 1 ? sb + OFF_W1 : ps == 2 ? sb + OFF_W2 : sb + OFF_W3;
-        const uint32_t rowb = ps == 0 ? 64u : 32u;              // bytes per pixel row of A / per output row of B
-        const uint32_t layout = ps == 0 ? 4u : 6u;              // 64-byte / 32-byte swizzle
-        const uint32_t n_rows = ps == 0 ? 80u : ps == 1 ? 64u : ps == 2 ? 48u : 32u;
-        const uint32_t w_tap_bytes = n_rows * rowb;
-        const uint32_t id = idesc[ps];
-        const uint32_t done_par = static_cast<uint32_t>((it * 4 + ps - 1) & 1);   // completion (it*4 + ps - 1) of o_ready
-        // Each completion of an o_ready barrier is waited for ONCE: as soon as this warp has issued tile t of this
-        // pass, tile t's epilogue may complete the barrier's NEXT phase, after which a second parity wait for the
-        // old phase would never return.
-        uint32_t seen = 0;
-#pragma unroll 1
-        for (int t = 0; t < NTILE; ++t) {
-          const int tx = t >> 1, ty = t & 1;
-          // dependencies: the epilogues whose output (or TMEM columns) this tile's MMAs touch
-          if (ps == 0) {
-            if (it > 0) mbar_wait(bars + DB_OREADY + t * 8, done_par);       // previous region's last epilogue of tile t
-          } else {
-            for (int t2 = 0; t2 < NTILE; ++t2) {
-              const int dx = (t2 >> 1) - tx;
-              if (dx >= -1 && dx <= 1 && !((seen >> t2) & 1u)) {
-                mbar_wait(bars + DB_OREADY + t2 * 8, done_par);
-                seen |= 1u << t2;
-              }
-            }
-          }
-          tc_fence_after();
-          const uint32_t d = tmem_base + static_cast<uint32_t>(t * NACC + ps * 16);
-          // Every pass uses the SAME pixel <-> accumulator-row grid (frame pixels [1,33) x [1,25)): the partial sums a
-          // pass leaves in TMEM belong to the pixel the next pass adds to.  Only the useful border shrinks per pass.
-          const uint32_t o_pix = static_cast<uint32_t>((16 * ty) * FP + 8 * tx);   // source pixel of tap (0,0)
-          if (elect_one()) {
-            const uint64_t adesc0 = make_kmajor_desc(a_base + o_pix * rowb, FP * rowb, layout);
-            const uint64_t bdesc0 = make_kmajor_desc(w_base, 8u * rowb, layout);
-            uint32_t acc = ps == 0 ? 0u : 1u;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-#pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                const uint64_t ad = adesc0 + static_cast<uint64_t>(((dy * FP + dx) * rowb) >> 4);
-                const uint64_t bd = bdesc0 + static_cast<uint64_t>(((dy * 3 + dx) * w_tap_bytes) >> 4);
-                umma_f16(d, ad, bd, id, acc);
-                acc = 1u;
-                if (ps == 0) umma_f16(d, ad + 2, bd + 2, id, 1u);   // second 16 channels of x
-              }
-            }
-            umma_commit(bars + DB_TFULL + t * 8);
-            if (ps == 0 && t == NTILE - 1) umma_commit(bars + DB_XEMPTY);   // X frame consumed: load the next one
-          }
-          __syncwarp();
-        }
-      }
+      dl.log(DBG_EV(1, it, 0, 0, 9));
+      issue_pass<0>(sb, bars, tmem_base, fmt, ty, it, dl);
+      if (elect_one()) umma_commit(bars + DB_XEMPTY);     // this row's reads of the X frame have retired
+      __syncwarp();
+      issue_pass<1>(sb, bars, tmem_base, fmt, ty, it, dl);
+      issue_pass<2>(sb, bars, tmem_base, fmt, ty, it, dl);
+      issue_pass<3>(sb, bars, tmem_base, fmt, ty, it, dl);
     }
-  } else if (warp < 4 || warp >= 8) {
-    // ===================================================== epilogue groups: tiles t = 2 * i + grp
-    const int grp = warp >= 8 ? 1 : 0;
+  } else if (warp < 12) {
+    // ===================================================== epilogue: group = tile column tx, both tile rows together
+    const int tx = warp >> 2;
     const int we = warp & 3;
     const int m = we * 32 + lane;             // accumulator row = pixel of the 8 x 16 tile
     const int th = m >> 3, tw = m & 7;
     const uint32_t lane_field = static_cast<uint32_t>(we * 32) << 16;
+    const uint32_t tcol0 = tmem_base + lane_field + static_cast<uint32_t>((2 * tx) * NACC);       // tile (tx, 0)
+    const uint32_t tcol1 = tcol0 + NACC;                                                          // tile (tx, 1)
     const uint16_t* in16 = static_cast<const uint16_t*>(p.in);
     uint16_t* out16 = static_cast<uint16_t*>(p.out);
     const int in_ctot = p.in_ctot, out_ctot = p.out_ctot, out_coff = p.out_coff;
+    const bool watch = !kBf16 && p.sat_flag != nullptr;
+    const int fx = 1 + 8 * tx + tw, fy0 = 1 + th, fy1 = 17 + th;      // frame pixels of this row in the two tiles
+    // 32-byte-swizzled store offsets of the two pixels inside an O array (bit 4 ^= bit 7; arrays are 256-byte aligned)
+    const uint32_t po0 = static_cast<uint32_t>(fy0 * FP + fx) * 32u, po1 = static_cast<uint32_t>(fy1 * FP + fx) * 32u;
+    const uint32_t sw0 = ((po0 >> 7) & 1u) << 4, sw1 = ((po1 >> 7) & 1u) << 4;
     uint32_t satm = 0;
+    DbgLog dl;
+    dl.init(p.dbg, 2 + tx, we == 0 && tx < 2);
     griddep_wait();   // the residual is read from the previous kernel's output
     int it = 0;
     for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
       const int b = region / per_img, r = region - b * per_img;
       const int ry = r / regions_x, rx = r - ry * regions_x;
-      const int gy0 = ry * RH - 4, gx0 = rx * RW - 4;       // global coordinates of frame pixel (0, 0)
+      const int gx = rx * RW - 4 + fx, gy_0 = ry * RH - 4 + fy0, gy_1 = gy_0 + 16;
+      const bool col_in = gx >= 0 && gx < W;
+      const bool img0 = col_in && gy_0 >= 0 && gy_0 < H, img1 = col_in && gy_1 >= 0 && gy_1 < H;
 #pragma unroll 1
-      for (int ps = 0; ps < 4; ++ps) {
+      for (int ps = 0; ps < 3; ++ps) {
+        // ---- o_ps of both tiles: bias + PReLU -> 16-bit -> shared memory (32-byte swizzled rows), zeros outside the image
         const uint32_t par = static_cast<uint32_t>((it * 4 + ps) & 1);
-#pragma unroll 1
-        for (int i = 0; i < NTILE / 2; ++i) {
-          const int t = 2 * i + grp;
-          const int tx = t >> 1, ty = t & 1;
-          const int fy = 1 + 16 * ty + th, fx = 1 + 8 * tx + tw;               // frame pixel of this row (all passes)
-          const int gy = gy0 + fy, gx = gx0 + fx;
-          const bool in_img = gy >= 0 && gy < H && gx >= 0 && gx < W;
-          const uint32_t tcol = tmem_base + lane_field + static_cast<uint32_t>(t * NACC);
-          if (ps < 3) {
-            // ---- o_ps: bias + PReLU -> 16-bit -> shared memory (32-byte swizzled rows), zeros outside the image
-            mbar_wait(bars + DB_TFULL + t * 8, par);
-            tc_fence_after();
-            uint32_t rr[16];
-            tmem_ld16(tcol + static_cast<uint32_t>(ps * 16), rr);
-            tmem_ld_wait();
-            const bool useful = fy >= 1 + ps && fy < FR - 1 - ps && fx >= 1 + ps && fx < FP - 1 - ps;
-            if (useful) {
-              const float* bs = s_bias + ps * 16;
-              const float* ss = s_slope + ps * 16;
-              uint32_t h[8];
+        mbar_wait(bars + DB_TFULL + (2 * tx) * 8, par);
+        mbar_wait(bars + DB_TFULL + (2 * tx + 1) * 8, par);
+        tc_fence_after();
+        dl.log(DBG_EV(2 + tx, it, ps, 2 * tx, 0));     // accumulators ready
+        uint32_t ra[16], rb[16];
+        tmem_ld16(tcol0 + static_cast<uint32_t>(ps * 16), ra);
+        tmem_ld16(tcol1 + static_cast<uint32_t>(ps * 16), rb);
+        tmem_ld_wait();
+        dl.log(DBG_EV(2 + tx, it, ps, 2 * tx, 1));     // TMEM read
+        const bool ux = fx >= 1 + ps && fx < FP - 1 - ps;
+        const bool use0 = ux && fy0 >= 1 + ps, use1 = ux && fy1 < FR - 1 - ps;      // fy0 <= 16, fy1 >= 17
+        const uint32_t obase = ps == 0 ? OFF_O0 : ps == 1 ? OFF_O1 : OFF_O2;
+        uint32_t h[8];
+        if (use0) {
+          bias_prelu_pack16<kBf16>(ra, s_bias + ps * 16, s_slope + ps * 16, h);
+          if (watch && img0) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float a0 = __uint_as_float(rr[2 * j]) + bs[2 * j];
-                float a1 = __uint_as_float(rr[2 * j + 1]) + bs[2 * j + 1];
-                a0 = a0 > 0.f ? a0 : a0 * ss[2 * j];
-                a1 = a1 > 0.f ? a1 : a1 * ss[2 * j + 1];
-                h[j] = in_img ? pack2<kBf16>(a0, a1) : 0u;
-              }
-              if (!kBf16 && p.sat_flag != nullptr) {
+            for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
+          }
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sg + obase + (po0 ^ sw0)) = img0 ? make_uint4(h[0], h[1], h[2], h[3]) : z;
+          *reinterpret_cast<uint4*>(sg + obase + ((po0 + 16u) ^ sw0)) = img0 ? make_uint4(h[4], h[5], h[6], h[7]) : z;
+        }
+        if (use1) {
+          bias_prelu_pack16<kBf16>(rb, s_bias + ps * 16, s_slope + ps * 16, h);
+          if (watch && img1) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
-              }
-              const uint32_t idx = static_cast<uint32_t>(fy * FP + fx);
-              const uint32_t off = (ps == 0 ? OFF_O0 : ps == 1 ? OFF_O1 : OFF_O2) + idx * 32u;
-              const uint32_t sw = ((off >> 7) & 1u) << 4;      // 32-byte swizzle: bit 4 ^= bit 7
-              *reinterpret_cast<uint4*>(sg + (off ^ sw)) = make_uint4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<uint4*>(sg + ((off + 16u) ^ sw)) = make_uint4(h[4], h[5], h[6], h[7]);
-            }
-            fence_proxy_async_smem();     // generic-proxy stores -> visible to the UMMAs of the next pass
+            for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
+          }
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sg + obase + (po1 ^ sw1)) = img1 ? make_uint4(h[0], h[1], h[2], h[3]) : z;
+          *reinterpret_cast<uint4*>(sg + obase + ((po1 + 16u) ^ sw1)) = img1 ? make_uint4(h[4], h[5], h[6], h[7]) : z;
+        }
+        fence_proxy_async_smem();     // generic-proxy stores -> visible to the UMMAs of the next pass
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + DB_OCOL + tx * 8);
+        dl.log(DBG_EV(2 + tx, it, ps, 2 * tx, 2));     // o_ps written + arrived
+      }
+      {
+        // ---- pass 3: o3 + x -> global (NHWC 16-bit channel slice), region interior only; 16 columns of both tiles at a time
+        const uint32_t par = static_cast<uint32_t>((it * 4 + 3) & 1);
+        const bool sx = fx >= 4 && fx < 4 + RW;
+        const bool st0 = img0 && sx && fy0 >= 4, st1 = img1 && sx && fy1 < 4 + RH;
+        const int64_t pix0 = (static_cast<int64_t>(b) * H + gy_0) * W + gx, pix1 = pix0 + static_cast<int64_t>(16) * W;
+        uint4 x0[4], x1[4];
+        if (st0) {
+          const uint4* src = reinterpret_cast<const uint4*>(in16 + pix0 * in_ctot);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x0[q] = __ldg(src + q);
+        }
+        if (st1) {
+          const uint4* src = reinterpret_cast<const uint4*>(in16 + pix1 * in_ctot);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x1[q] = __ldg(src + q);
+        }
+        mbar_wait(bars + DB_TFULL + (2 * tx) * 8, par);
+        mbar_wait(bars + DB_TFULL + (2 * tx + 1) * 8, par);
+        tc_fence_after();
+        dl.log(DBG_EV(2 + tx, it, 3, 2 * tx, 0));
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t ra[16], rb[16];
+          tmem_ld16(tcol0 + static_cast<uint32_t>(48 + 16 * half), ra);
+          tmem_ld16(tcol1 + static_cast<uint32_t>(48 + 16 * half), rb);
+          tmem_ld_wait();
+          if (half == 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + DB_OREADY + t * 8);
-          } else {
-            // ---- o3 + x -> global (NHWC 16-bit channel slice), region interior only
-            const bool store = in_img && fy >= 4 && fy < 4 + RH && fx >= 4 && fx < 4 + RW;
-            const int64_t pix = (static_cast<int64_t>(b) * H + gy) * W + gx;
-            uint4 xr[4];
-            if (store) {
-              const uint4* src = reinterpret_cast<const uint4*>(in16 + pix * in_ctot);
+            if (lane == 0) mbar_arrive(bars + DB_OCOL + tx * 8);      // TMEM columns of both tiles are free again
+            dl.log(DBG_EV(2 + tx, it, 3, 2 * tx, 1));
+          }
+          uint32_t h[8];
+          if (st0) {
+            bias_prelu_res_pack16<kBf16>(ra, s_bias + 48 + 16 * half, s_slope + 48 + 16 * half, x0[2 * half], x0[2 * half + 1], h);
+            if (watch) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) xr[q] = __ldg(src + q);
+              for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
             }
-            mbar_wait(bars + DB_TFULL + t * 8, par);
-            tc_fence_after();
-            uint32_t r0[16], r1[16];
-            tmem_ld16(tcol + 48u, r0);
-            tmem_ld16(tcol + 64u, r1);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + DB_OREADY + t * 8);     // TMEM columns of tile t are free again
-            if (store) {
-              const float* bs = s_bias + 48;
-              const float* ss = s_slope + 48;
-              const uint32_t* xw = reinterpret_cast<const uint32_t*>(xr);
-              uint32_t h[16];
+            uint4* dst = reinterpret_cast<uint4*>(out16 + pix0 * out_ctot + out_coff + 16 * half);
+            dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+            dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+          }
+          if (st1) {
+            bias_prelu_res_pack16<kBf16>(rb, s_bias + 48 + 16 * half, s_slope + 48 + 16 * half, x1[2 * half], x1[2 * half + 1], h);
+            if (watch) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const uint32_t ra = j < 8 ? r0[2 * j] : r1[2 * j - 16];
-                const uint32_t rb = j < 8 ? r0[2 * j + 1] : r1[2 * j - 15];
-                float a0 = __uint_as_float(ra) + bs[2 * j];
-                float a1 = __uint_as_float(rb) + bs[2 * j + 1];
-                a0 = a0 > 0.f ? a0 : a0 * ss[2 * j];
-                a1 = a1 > 0.f ? a1 : a1 * ss[2 * j + 1];
-                a0 += cvt_lo<kBf16>(xw[j]);
-                a1 += cvt_hi<kBf16>(xw[j]);
-                h[j] = pack2<kBf16>(a0, a1);
-              }
-              if (!kBf16 && p.sat_flag != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) satm = sat_track(satm, h[j]);
-              }
-              uint4* dst = reinterpret_cast<uint4*>(out16 + pix * out_ctot + out_coff);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) dst[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+              for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
             }
+            uint4* dst = reinterpret_cast<uint4*>(out16 + pix1 * out_ctot + out_coff + 16 * half);
+            dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+            dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
           }
         }
+        dl.log(DBG_EV(2 + tx, it, 3, 2 * tx, 2));
       }
     }
     if (!kBf16) sat_report(p.sat_flag, satm);
@@ -329,7 +422,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 6) {
+  if (warp == W_ALLOC) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
@@ -386,6 +479,7 @@ int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_
   for (int j = 0; j < 4; ++j) f.bias[j] = a.bias[j], f.slope[j] = a.slope[j];
   f.in = a.in, f.in_ctot = a.in_ctot, f.out = a.out, f.out_ctot = a.out_ctot, f.out_coff = a.out_coff;
   f.sat_flag = a.sat_flag;
+  f.dbg = reinterpret_cast<long long*>(a.timeline);
   const CUtensorMapDataType dt = f.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   uint32_t estr[5] = {1, 1, 1, 1, 1};
   {

@@ -492,6 +492,7 @@ struct __align__(64) FusedParams {
   void* out;
   int out_ctot, out_coff;
   int* sat_flag;
+  long long* dbg;                // optional timeline buffer (tools/dense_block_timeline.py): CTA 0 logs (event, clock64)
 };
 
 // A fully resolved launch: kernel variant, launch geometry and the parameter block (with its encoded tensor maps).
