@@ -24,12 +24,15 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from ._lib import IgemmArgs
+from ._lib import DenseBlockArgs, IgemmArgs
 
 __all__ = ["RDUNet", "RDUNet_T", "init_weights", "ForwardPlan", "DEFAULT_PREC"]
 
 DEFAULT_PREC = os.environ.get("B200DN_PREC", "bf16")
 _USE_GRAPH = os.environ.get("B200DN_GRAPH", "1") != "0"   # replay nn.Module forwards as one CUDA graph from the 2nd call on
+# 32-channel DenoisingBlocks (level 0 of base_filters = 32) run as ONE fused kernel instead of four launches
+_FUSE_DENSE = os.environ.get("B200DN_FUSED_DENSE", "1") != "0"
+MODE_DENSE_BLOCK = 4     # layer_info "mode" of a fused block (the per-layer modes are _lib.MODE_*)
 
 
 # --------------------------------------------------------------------------- init
@@ -366,7 +369,44 @@ class ForwardPlan:
                                     flops=2 * pix * taps * cin * cout, nchw=nchw))
         return a
 
+    def _fusable(self, C: int) -> bool:
+        return _FUSE_DENSE and C == 32 and self.prec in (_lib.PREC_BF16, _lib.PREC_FP16)
+
+    def _dense_fused(self, blk: _Params, src: _Act, dst: _Act, dst_coff: int, B, H, W, C) -> None:
+        """One b200dn_dense_block launch: input-stationary passes, partial sums in TMEM, o0..o2 never leave the SM."""
+        convs = [getattr(blk, f"conv_{k}") for k in range(4)]
+        ws = []
+        for c in convs:
+            w = c.weight.detach().to(torch.float32).contiguous()
+            self._keep.append(w)
+            ws.append(w)
+        nbytes = self.lib.b200dn_dense_block_weight_bytes(C)
+        packed = torch.empty(nbytes // 2, dtype=torch.int16, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.b200dn_pack_dense_block_weights(ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(),
+                                                            ws[3].data_ptr(), C, self.prec, packed.data_ptr(), stream),
+                   "pack_dense_block_weights")
+        self._keep.append(packed)
+        a = DenseBlockArgs()
+        a.prec, a.B, a.H, a.W, a.channels = self.prec, B, H, W, C
+        a.in_, a.in_ctot = src.hi.data_ptr(), src.ctot
+        a.out, a.out_ctot, a.out_coff = dst.hi.data_ptr(), dst.ctot, dst_coff
+        a.wfused = packed.data_ptr()
+        for k in range(4):
+            a.bias[k] = self._f32(convs[k].bias, self._keep)
+            a.slope[k] = self._f32(getattr(blk, f"actv_{k}").weight, self._keep)
+        if self.sat_flag is not None:
+            a.sat_flag = self.sat_flag.data_ptr()
+        g = C // 2
+        flops = 2 * B * H * W * 9 * (C * g + (C + g) * g + (C + 2 * g) * g + (C + 3 * g) * C)
+        self.flops += flops
+        self.launches.append(a)
+        self.layer_info.append(dict(mode=MODE_DENSE_BLOCK, H=H, W=W, cin=C, cout=C, flops=flops, nchw=False))
+
     def _dense(self, blk: _Params, src: _Act, dst: _Act, dst_coff: int, B, H, W, C) -> None:
+        if self._fusable(C):
+            self._dense_fused(blk, src, dst, dst_coff, B, H, W, C)
+            return
         g = C // 2
         for k in range(3):
             self._igemm(_lib.MODE_CONV3X3, getattr(blk, f"conv_{k}"), getattr(blk, f"actv_{k}"),
@@ -379,8 +419,11 @@ class ForwardPlan:
         ch = [F << l for l in range(4)]
         hs = [H >> l for l in range(4)]
         ws = [W >> l for l in range(4)]
-        Da = [_Act(B, hs[l], ws[l], ch[l] * 5 // 2, two, dev) for l in range(4)]
-        Db = [_Act(B, hs[l], ws[l], ch[l] * 5 // 2, two, dev) for l in range(4)]
+        # dense buffers [x | o0 | o1 | o2] of 2.5 C channels; a level whose blocks run fused keeps o0..o2 on the SM and
+        # needs only the C channels of x (no channel-prefix reads of a wider pixel: the TMA frame is dense)
+        dch = [ch[l] if self._fusable(ch[l]) else ch[l] * 5 // 2 for l in range(4)]
+        Da = [_Act(B, hs[l], ws[l], dch[l], two, dev) for l in range(4)]
+        Db = [_Act(B, hs[l], ws[l], dch[l], two, dev) for l in range(4)]
         K = [_Act(B, hs[l], ws[l], ch[l] * 3, two, dev) for l in range(3)]
         I0 = _Act(B, H, W, F, two, dev)
         self.bufs = dict(Da=Da, Db=Db, K=K, I0=I0)
@@ -423,10 +466,13 @@ class ForwardPlan:
         n = len(self.launches)
         self._handles = (C.c_void_p * n)()
         for i, a in enumerate(self.launches):
-            if a.out_kind == _lib.OUT_NCHW32:      # bound per call in run(); prepare wants a non-null placeholder
-                a.out_nchw = self._keep[0].data_ptr()
             h = C.c_void_p()
-            _lib.check(self.lib.b200dn_igemm_prepare(C.byref(a), C.byref(h)), f"igemm_prepare (launch {i})")
+            if isinstance(a, DenseBlockArgs):
+                _lib.check(self.lib.b200dn_dense_block_prepare(C.byref(a), C.byref(h)), f"dense_block_prepare (launch {i})")
+            else:
+                if a.out_kind == _lib.OUT_NCHW32:      # bound per call in run(); prepare wants a non-null placeholder
+                    a.out_nchw = self._keep[0].data_ptr()
+                _lib.check(self.lib.b200dn_igemm_prepare(C.byref(a), C.byref(h)), f"igemm_prepare (launch {i})")
             self._handles[i] = h
         self._out_handle = self._handles[n - 1]
         self._ready = torch.cuda.Event()
