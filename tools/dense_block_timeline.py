@@ -43,8 +43,13 @@ t = tl.cpu().tolist()
 ev = []
 for r in range(3):
     base = r * 2730
-    for i in range(min(int(t[base]), 1360)):
-        ev.append((t[base + 3 + 2 * i], t[base + 2 + 2 * i]))
+    for it in range(16):
+        for ps in range(4):
+            for tile in range(6):
+                for kind in range(4):
+                    clk = t[base + 2 + it * 160 + ps * 40 + tile * 4 + kind]
+                    if clk:
+                        ev.append((clk, (r + 1) * 100000 + it * 1000 + ps * 100 + tile * 10 + (9 if kind == 3 else kind)))
 ev.sort()
 n = len(ev)
 t0 = ev[0][0]
@@ -56,5 +61,5 @@ for clk, e in ev:
     it, rest = divmod(rest, 1000)
     ps, rest = divmod(rest, 100)
     tile, kind = divmod(rest, 10)
-    if it in (1, 2):
+    if it in (3, 4):
         print(f"{clk - t0:8d}  {names[role]} region {it} pass {ps} tile {tile}  {kinds[role].get(kind, kind)}")

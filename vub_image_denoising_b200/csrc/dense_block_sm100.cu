@@ -85,32 +85,29 @@ __device__ __forceinline__ void tmem_alloc_all(uint32_t dst_smem) { tmem_alloc(d
 // (event id, clock) pairs to ITS OWN third of a global buffer with plain stores (no atomics: a logged event costs a
 // clock read and two fire-and-forget stores).  Layout: role r in {1,2,3} owns entries [(r-1)*1365, r*1365); slot 0 of
 // each third holds the count.
+template <bool kDbg>
 struct DbgLog {
   long long* base;
-  int n;
   __device__ __forceinline__ void init(long long* dbg, int role, bool active) {
-    base = (dbg != nullptr && active && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? dbg + (role - 1) * 2730 : nullptr;
-    n = 0;
+    base = (kDbg && dbg != nullptr && active && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? dbg + (role - 1) * 2730 : nullptr;
   }
-  __device__ __forceinline__ void log(int ev) {
-    if (base != nullptr && n < 1360) {
-      base[2 + 2 * n] = ev;
-      base[3 + 2 * n] = clock64();
-      ++n;
-      base[0] = n;
+  // one fire-and-forget store per event: slot = f(region, pass, tile, kind), regions 0..15 only.  Compiled out of the
+  // production kernel (kDbg = false): the slot arithmetic alone cost the issuer warps ~100 instructions per tile.
+  __device__ __forceinline__ void log(int role, int it, int ps, int t, int kind) {
+    if (kDbg) {
+      if (base != nullptr && it < 16) base[2 + it * 160 + ps * 40 + t * 4 + (kind == 9 ? 3 : kind)] = clock64();
     }
   }
 };
-// event ids: role * 100000 + region_local * 1000 + pass * 100 + tile * 10 + kind
-#define DBG_EV(role, it, ps, t, kind) ((role) * 100000 + (it) * 1000 + (ps) * 100 + (t) * 10 + (kind))
+#define DBG_EV(role, it, ps, t, kind) (role), (it), (ps), (t), (kind)
 
 // One pass of one tile row: for each of the three tiles, wait for the epilogues its MMAs depend on, then issue the nine
 // taps (x 2 k16 steps in pass 0) with compile-time descriptor offsets and commit to the tile's t_full barrier.
 // Every pass uses the SAME pixel <-> accumulator-row grid (frame pixels [1,33) x [1,25)): the partial sums a pass leaves
 // in TMEM belong to the pixel the next pass adds to; only the useful border shrinks per pass.
-template <int PS>
+template <int PS, bool kDbg>
 __device__ __forceinline__ void issue_pass(uint32_t sb, uint32_t bars, uint32_t tmem_base, uint32_t fmt, int ty, int it,
-                                           DbgLog& dl) {
+                                           DbgLog<kDbg>& dl) {
   constexpr uint32_t rowb = PS == 0 ? 64u : 32u;              // bytes per pixel row of A / per output row of B
   constexpr uint32_t layout = PS == 0 ? 4u : 6u;              // 64-byte / 32-byte swizzle
   constexpr uint32_t n_rows = PS == 0 ? 80u : PS == 1 ? 64u : PS == 2 ? 48u : 32u;
@@ -197,7 +194,7 @@ __device__ __forceinline__ void bias_prelu_res_pack16(const uint32_t (&rr)[16], 
   }
 }
 
-template <bool kBf16>
+template <bool kBf16, bool kDbg>
 __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -274,19 +271,19 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     // timeline of the first version showed the tensor pipe idle behind it; two issuers and compile-time tap offsets)
     const int ty = warp - W_ISSUER0;
     const uint32_t fmt = static_cast<uint32_t>(p.fmt);
-    DbgLog dl;
+    DbgLog<kDbg> dl;
     dl.init(p.dbg, 1, ty == 0);
     mbar_wait(bars + DB_W, 0);
     int it = 0;
     for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
       mbar_wait(bars + DB_XFULL, static_cast<uint32_t>(it & 1));
       dl.log(DBG_EV(1, it, 0, 0, 9));
-      issue_pass<0>(sb, bars, tmem_base, fmt, ty, it, dl);
+      issue_pass<0, kDbg>(sb, bars, tmem_base, fmt, ty, it, dl);
       if (elect_one()) umma_commit(bars + DB_XEMPTY);     // this row's reads of the X frame have retired
       __syncwarp();
-      issue_pass<1>(sb, bars, tmem_base, fmt, ty, it, dl);
-      issue_pass<2>(sb, bars, tmem_base, fmt, ty, it, dl);
-      issue_pass<3>(sb, bars, tmem_base, fmt, ty, it, dl);
+      issue_pass<1, kDbg>(sb, bars, tmem_base, fmt, ty, it, dl);
+      issue_pass<2, kDbg>(sb, bars, tmem_base, fmt, ty, it, dl);
+      issue_pass<3, kDbg>(sb, bars, tmem_base, fmt, ty, it, dl);
     }
   } else if (warp < 12) {
     // ===================================================== epilogue: group = tile column tx, both tile rows together
@@ -306,7 +303,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     const uint32_t po0 = static_cast<uint32_t>(fy0 * FP + fx) * 32u, po1 = static_cast<uint32_t>(fy1 * FP + fx) * 32u;
     const uint32_t sw0 = ((po0 >> 7) & 1u) << 4, sw1 = ((po1 >> 7) & 1u) << 4;
     uint32_t satm = 0;
-    DbgLog dl;
+    DbgLog<kDbg> dl;
     dl.init(p.dbg, 2 + tx, we == 0 && tx < 2);
     griddep_wait();   // the residual is read from the previous kernel's output
     int it = 0;
@@ -510,16 +507,18 @@ int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_
     }
     woff += static_cast<uint64_t>(kdim[ps]) * ndim[ps] * 9 * 2;
   }
-  static const void* const kernels[2] = {reinterpret_cast<const void*>(dense_block_kernel<false>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<true>)};
-  if (int rc = ensure_max_dyn_smem(g_dense_opt_in, kernels, 2, DSMEM_BYTES, "cudaFuncSetAttribute(dense_block_kernel, smem)"))
+  static const void* const kernels[4] = {reinterpret_cast<const void*>(dense_block_kernel<false, false>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<true, false>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<false, true>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<true, true>)};
+  if (int rc = ensure_max_dyn_smem(g_dense_opt_in, kernels, 4, DSMEM_BYTES, "cudaFuncSetAttribute(dense_block_kernel, smem)"))
     return rc;
   int sms = device_sm_count();
   if (sms <= 0) return B200DN_E_CUDA;
   int grid = f.num_regions < sms ? f.num_regions : sms;
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
   cfg->kind = 1;
-  cfg->kernel = kernels[f.fmt];
+  cfg->kernel = kernels[f.fmt + (f.dbg != nullptr ? 2 : 0)];
   cfg->grid = grid;
   cfg->threads = DTHREADS;
   cfg->smem = DSMEM_BYTES;
