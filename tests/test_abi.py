@@ -56,6 +56,29 @@ def test_igemm_args_field_offsets_match_the_header(built_lib):
     assert [getattr(_lib.IgemmArgs, n).offset for n in py_names] == offs
 
 
+def test_dense_block_args_layout_matches_the_header(built_lib):
+    """struct b200dn_dense_block_args: size and every field offset of the ctypes mirror vs the C compiler."""
+    c_names = ["prec", "B", "H", "W", "channels", "in", "in_ctot", "out", "out_ctot", "out_coff", "wfused", "bias", "slope",
+               "max_ctas", "sat_flag", "timeline"]
+    body = "".join(f'printf("%zu ", offsetof(b200dn_dense_block_args, {n}));' for n in c_names)
+    body += 'printf("%zu", sizeof(b200dn_dense_block_args));'
+    src = f'#include "b200dn.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){{{body}return 0;}}'
+    exe = ROOT / "vub_image_denoising_b200" / "build" / "offsets_dense"
+    exe.parent.mkdir(exist_ok=True)
+    subprocess.run(["gcc", "-x", "c", "-", "-I", str(ROOT / "include"), "-o", str(exe)], input=src, text=True, check=True)
+    vals = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    py_names = [n for n, _ in _lib.DenseBlockArgs._fields_]
+    assert [n.rstrip("_") for n in py_names] == c_names
+    assert [getattr(_lib.DenseBlockArgs, n).offset for n in py_names] == vals[:-1]
+    assert ctypes.sizeof(_lib.DenseBlockArgs) == vals[-1]
+    assert built_lib.b200dn_dense_block_weight_bytes(32) == 9 * (80 * 32 + 64 * 16 + 48 * 16 + 32 * 16) * 2
+    assert built_lib.b200dn_dense_block_weight_bytes(64) < 0          # only the 32-channel block is fused
+    a = _lib.DenseBlockArgs()
+    h = ctypes.c_void_p(1)
+    assert built_lib.b200dn_dense_block_prepare(ctypes.byref(a), ctypes.byref(h)) == -1 and h.value is None
+    assert b"dense_block" in built_lib.b200dn_last_error()
+
+
 def test_packed_weight_bytes(built_lib):
     f = built_lib.b200dn_packed_weight_bytes
     assert f(16, 16, 9, _lib.PREC_BF16) == 9 * 16 * 64 * 2          # cin padded to 64

@@ -255,3 +255,82 @@ def test_igemm_argument_errors(built_lib):
     with pytest.raises(RuntimeError, match="lo activation plane"):
         torch.ops.b200dn.conv_igemm(x_ok, None, wp, b, b, _lib.MODE_CONV3X3, _lib.PREC_BF16X2, 16, 16, out, None, 0,
                                     None, None)
+
+
+# ----------------------------------------------------------------------------------------------- fused dense block
+def _dense_block_ref(x16, ws, bs, ss, dt):
+    """fp64 evaluation of a DenoisingBlock (UNet/RDUNet_model.py:95-115) with the kernel's rounding points: 16-bit
+    weights and inputs, o0..o2 rounded to the 16-bit storage type before they feed the next conv, fp64 accumulation."""
+    cat = x16.double()
+    for j in range(3):
+        o = F.prelu(F.conv2d(cat, ws[j].to(dt).double(), bs[j].double(), padding=1), ss[j].double())
+        cat = torch.cat([cat, o.to(dt).double()], 1)
+    return F.prelu(F.conv2d(cat, ws[3].to(dt).double(), bs[3].double(), padding=1), ss[3].double()) + x16.double()
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_FP16, _lib.PREC_BF16], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(1, 26, 18), (1, 8, 8), (2, 64, 64), (3, 40, 72), (1, 27, 19), (2, 136, 56)])
+def test_fused_dense_block(shape, prec, built_lib):
+    """b200dn_dense_block (one launch: input-stationary passes, partial sums in TMEM) against the fp64 block and
+    against the four per-layer launches it replaces.  Shapes: exactly one 18 x 26 region, an image smaller than a
+    region, several regions with partial ones at the right / bottom borders, odd batch."""
+    import ctypes as C
+    B, H, W = shape
+    L = _lib.lib()
+    dt = dt16(prec)
+    st = torch.cuda.current_stream().cuda_stream
+    x = (_rand(B, H, W, 48, seed=B + H, scale=0.5)).to(dt)                       # block input = channels [0, 32) of a 48-ch buffer
+    ws = [_rand(co, ci, 3, 3, seed=10 + j, scale=(2.0 / (9 * ci)) ** 0.5) for j, (co, ci) in enumerate(((16, 32), (16, 48), (16, 64), (32, 80)))]
+    bs = [_rand(co, seed=20 + j, scale=0.1) for j, co in enumerate((16, 16, 16, 32))]
+    ss = [torch.full((co,), 0.25, device=DEV) + _rand(co, seed=30 + j, scale=0.05) for j, co in enumerate((16, 16, 16, 32))]
+    wf = torch.empty(L.b200dn_dense_block_weight_bytes(32) // 2, dtype=torch.int16, device=DEV)
+    _lib.check(L.b200dn_pack_dense_block_weights(ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), ws[3].data_ptr(), 32, prec,
+                                                 wf.data_ptr(), st))
+    out = torch.full((B, H, W, 72), 7.0, device=DEV, dtype=dt)                   # writes the slice [40, 72)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    a = _lib.DenseBlockArgs()
+    a.prec, a.B, a.H, a.W, a.channels = prec, B, H, W, 32
+    a.in_, a.in_ctot = x.data_ptr(), 48
+    a.out, a.out_ctot, a.out_coff = out.data_ptr(), 72, 40
+    a.wfused = wf.data_ptr()
+    for j in range(4):
+        a.bias[j], a.slope[j] = bs[j].data_ptr(), ss[j].data_ptr()
+    a.sat_flag = flag.data_ptr()
+    h = C.c_void_p()
+    _lib.check(L.b200dn_dense_block_prepare(C.byref(a), C.byref(h)), "dense_block_prepare")
+    _lib.check(L.b200dn_igemm_launch(h, st), "launch")
+    _lib.check(L.b200dn_igemm_launch(h, st), "launch")          # relaunching a prepared block is idempotent
+    torch.cuda.synchronize()
+    L.b200dn_igemm_release(h)
+    ref = _dense_block_ref(x[..., :32].permute(0, 3, 1, 2), ws, bs, ss, dt).cpu()
+    got = out[..., 40:72].permute(0, 3, 1, 2).double().cpu()
+    ulp = 2.0 ** -10 if prec == _lib.PREC_FP16 else 2.0 ** -7
+    err = (got - ref).abs()
+    # one storage ulp of the result + a rounding flip of an intermediate o_k (a 16-bit ulp times a weight) per stage
+    tol = ref.abs() * ulp * 2 + 6 * ulp
+    assert not (err > tol).any(), f"{int((err > tol).sum())} / {err.numel()} outside tolerance, max err {float(err.max()):.3e}"
+    assert torch.all(out[..., :40].float() == 7.0), "wrote outside its channel slice"
+    assert int(flag.item()) == 0
+    with pytest.raises(RuntimeError, match="overlaps"):
+        a.out, a.out_ctot, a.out_coff = x.data_ptr(), 48, 0
+        _lib.check(L.b200dn_dense_block_prepare(C.byref(a), C.byref(h)), "dense_block_prepare")
+
+
+def test_fused_and_per_layer_networks_agree(built_lib, monkeypatch):
+    """RDUNet_T(32) with the level-0 blocks fused vs launched layer by layer: same 16-bit rounding points, different
+    fp32 summation order -> the two forwards agree to a few 16-bit ulps of the activations."""
+    import vub_image_denoising_b200 as b2
+    from vub_image_denoising_b200 import rdunet
+    torch.manual_seed(5)
+    net = b2.RDUNet(base_filters=32).to(DEV).eval()
+    net.precision = "fp16"
+    x = torch.rand(2, 3, 64, 80, device=DEV) * 2 - 1
+    with torch.no_grad():
+        fused = net(x)
+        plan = net.plan(2, 64, 80)
+        assert sum(isinstance(a, _lib.DenseBlockArgs) for a in plan.launches) == 4 and len(plan.launches) == 68 - 12
+        monkeypatch.setattr(rdunet, "_FUSE_DENSE", False)
+        net.invalidate_plans()
+        layered = net(x)
+        assert len(net.plan(2, 64, 80).launches) == 68
+    assert float((fused - layered).abs().max()) < 5e-3

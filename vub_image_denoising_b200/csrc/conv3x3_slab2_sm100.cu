@@ -103,7 +103,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   griddep_launch_dependents();
-  griddep_wait();
+  // the W producer only reads the packed weights (static data): it fills its ring while the previous kernel of the
+  // stream is still running; every other role touches activations and waits for it
+  if (warp != 2) griddep_wait();
 
   const int num_pair_tiles = p.num_tiles;   // pair tiles
   const int block_n = p.block_n, half_n = p.block_n >> 1;

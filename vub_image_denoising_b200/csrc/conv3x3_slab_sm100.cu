@@ -98,7 +98,7 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
   // the stream; let the next kernel start its own prologue on idle SMs, then wait for our producer to finish before
   // any activation memory is touched (packed weights / bias are static and need no wait).
   griddep_launch_dependents();
-  if (!(WRES && warp == 2)) griddep_wait();
+  if (warp != 2) griddep_wait();   // the W producer (resident or streamed) only reads static data
 
   const int num_tiles = p.num_tiles, grid = gridDim.x;
   const int num_n_tiles = p.num_n_tiles, n_tiles_per_group = p.n_tiles_per_group, block_n = p.block_n;

@@ -107,7 +107,7 @@ igemm_kernel(const __grid_constant__ KParams p) {
   // the stream; let the next kernel start its own prologue on idle SMs, then wait for our producer to finish before
   // any activation memory is touched (packed weights / bias are static and need no wait).
   griddep_launch_dependents();
-  griddep_wait();
+  if (warp != 2) griddep_wait();   // the W producer only reads static data: it runs ahead of the previous kernel's tail
 
   // Loop-invariant parameters live in registers: every asm volatile("memory") below would otherwise force the
   // compiler to re-read them from the constant bank inside the issue loops.
