@@ -36,26 +36,56 @@ constexpr int SMEM_BYTES_SLAB2 = 1024 + DATA_BYTES + SLAB_CTRL_BYTES + 2 * 2 * M
 constexpr uint32_t B_SLAB_FULL = 0, B_SLAB_EMPTY = 64, B_W_FULL = 128, B_W_EMPTY = 192, B_TFULL = 256, B_TEMPTY = 272,
                    B_TMEM_PTR = 288;
 
-// spatial super tile `m_tile` (or an all-out-of-bounds tile past the end, for the odd CTA of the last pair)
-__device__ __forceinline__ TileCoord decode_pair_tile(int pair_tile, int rank, const KParams& p, int tile_w, int tile_h) {
-  TileCoord t;
-  const int m_pair = pair_tile / p.num_n_tiles;
-  const int nt = pair_tile - m_pair * p.num_n_tiles;
-  t.grp = 0;
-  t.n0 = nt * p.block_n;
-  const int m_tile = 2 * m_pair + rank;
-  if (m_tile >= p.num_m_tiles) {
-    t.b = 0, t.x0 = 0, t.y0 = p.tiles_y * tile_h;   // >= H: TMA zero-fills, the epilogue masks every pixel
+// Division-free walk over the pair tiles cluster_id, cluster_id + num_clusters, ... : pair tile = (m_pair, N tile), this
+// CTA's spatial super tile is m_tile = 2 * m_pair + rank (an all-out-of-bounds tile past the end for the odd CTA of the
+// last pair).  The strides are decomposed once into (tile column, tile row, image) digits and added with carries.
+struct PairWalker {
+  int nt, tx, ty, b;
+  int s_nt, d_tx, d_ty, d_b, e_tx, e_ty, e_b;   // stride digits: N tile; 2 * pair stride; the extra 2 on an N-tile carry
+  int num_n_tiles, tiles_x, tiles_y, images;
+  __device__ __forceinline__ static void split(int m, int tiles_x, int tiles_y, int& tx, int& ty, int& b) {
+    const int q = m / tiles_x;
+    tx = m - q * tiles_x;
+    b = q / tiles_y;
+    ty = q - b * tiles_y;
+  }
+  __device__ __forceinline__ void init(int pair_tile, int stride, int rank, const KParams& p) {
+    num_n_tiles = p.num_n_tiles, tiles_x = p.tiles_x, tiles_y = p.tiles_y, images = p.B;
+    const int m_pair = pair_tile / num_n_tiles;
+    nt = pair_tile - m_pair * num_n_tiles;
+    split(2 * m_pair + rank, tiles_x, tiles_y, tx, ty, b);
+    const int s_pair = stride / num_n_tiles;
+    s_nt = stride - s_pair * num_n_tiles;
+    split(2 * s_pair, tiles_x, tiles_y, d_tx, d_ty, d_b);
+    split(2, tiles_x, tiles_y, e_tx, e_ty, e_b);
+  }
+  __device__ __forceinline__ void add(int ax, int ay, int ab) {
+    tx += ax;
+    int c = tx >= tiles_x ? 1 : 0;
+    tx -= c ? tiles_x : 0;
+    ty += ay + c;
+    c = ty >= tiles_y ? 1 : 0;
+    ty -= c ? tiles_y : 0;
+    b += ab + c;
+  }
+  __device__ __forceinline__ void next() {
+    nt += s_nt;
+    const bool carry = nt >= num_n_tiles;
+    nt -= carry ? num_n_tiles : 0;
+    add(d_tx, d_ty, d_b);
+    if (carry) add(e_tx, e_ty, e_b);
+  }
+  __device__ __forceinline__ TileCoord coord(int block_n, int tile_w, int tile_h) const {
+    TileCoord t;
+    t.grp = 0, t.n0 = nt * block_n;
+    if (b >= images) {
+      t.b = 0, t.x0 = 0, t.y0 = tiles_y * tile_h;   // >= H: TMA zero-fills, the epilogue masks every pixel
+    } else {
+      t.b = b, t.y0 = ty * tile_h, t.x0 = tx * tile_w;
+    }
     return t;
   }
-  const int per_img = p.tiles_x * p.tiles_y;
-  t.b = m_tile / per_img;
-  const int r = m_tile - t.b * per_img;
-  const int ty = r / p.tiles_x;
-  t.y0 = ty * tile_h;
-  t.x0 = (r - ty * p.tiles_x) * tile_w;
-  return t;
-}
+};
 
 template <int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __grid_constant__ KParams p) {
@@ -120,8 +150,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
     int s = 0;
     uint32_t sph = 0;
     const int pa0 = p.pair_a[0], pa1 = p.pair_a[1], pa2 = p.pair_a[2];
-    for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters) {
-      const TileCoord t = decode_pair_tile(tile, rank, p, TW, STH);
+    PairWalker pw_;
+    pw_.init(cluster_id, num_clusters, rank, p);
+    for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters, pw_.next()) {
+      const TileCoord t = pw_.coord(block_n, TW, STH);
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int pa = pair == 0 ? pa0 : pair == 1 ? pa1 : pa2;
         const CUtensorMap* tmA = pa ? &p.tmA1 : &p.tmA0;
@@ -147,8 +179,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
     const int w_taps = p.w_taps;
     const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128 * w_taps);   // both halves of w_taps tap tiles
     const int pw0 = p.pair_w[0] * 9, pw1 = p.pair_w[1] * 9, pw2 = p.pair_w[2] * 9;
-    for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters) {
-      const TileCoord t = decode_pair_tile(tile, rank, p, TW, STH);
+    PairWalker pw_;
+    pw_.init(cluster_id, num_clusters, rank, p);
+    for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters, pw_.next()) {
+      const TileCoord t = pw_.coord(block_n, TW, STH);
       const int n_row = t.n0 + rank * half_n;
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int wbase = pair == 0 ? pw0 : pair == 1 ? pw1 : pw2;
@@ -237,8 +271,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
     if (one_n_tile) stage_bias_slope(epi_bias, epi_slope, bias, slope, 0, block_n, cout, et);
     int local_tile = 0;
     uint32_t satm = 0;
-    for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters, ++local_tile) {
-      const TileCoord t = decode_pair_tile(tile, rank, p, TW, STH);
+    PairWalker pw_;
+    pw_.init(cluster_id, num_clusters, rank, p);
+    for (int tile = cluster_id; tile < num_pair_tiles; tile += num_clusters, ++local_tile, pw_.next()) {
+      const TileCoord t = pw_.coord(block_n, TW, STH);
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (local_tile >> 1) & 1;
       // bias / PReLU slopes of the tile's N range: staged once when the layer has a single N tile (per-tile global

@@ -114,8 +114,10 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
     int s = 0;
     uint32_t sph = 0;
     const int pa0 = p.pair_a[0], pa1 = p.pair_a[1], pa2 = p.pair_a[2];
-    for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
-      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
+    TileWalker tw_;
+    tw_.init(blockIdx.x, grid, num_n_tiles, tiles_x, tiles_y);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, tw_.next()) {
+      const TileCoord t = tw_.coord(block_n, TW, STH);
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int pa = pair == 0 ? pa0 : pair == 1 ? pa1 : pa2;
         const CUtensorMap* tmA = pa ? &p.tmA1 : &p.tmA0;
@@ -156,8 +158,10 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
     const int w_taps = p.w_taps;
     const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128 * w_taps);   // one box = w_taps tap tiles
     const int pw0 = p.pair_w[0] * 9, pw1 = p.pair_w[1] * 9, pw2 = p.pair_w[2] * 9;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
-      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
+    TileWalker tw_;
+    tw_.init(blockIdx.x, grid, num_n_tiles, tiles_x, tiles_y);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, tw_.next()) {
+      const TileCoord t = tw_.coord(block_n, TW, STH);
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int wbase = pair == 0 ? pw0 : pair == 1 ? pw1 : pw2;
         for (int cb = 0; cb < n_cblk; ++cb) {
@@ -272,8 +276,10 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
     if (one_n_tile) stage_bias_slope(epi_bias, epi_slope, bias, slope, 0, block_n, cout, et, EPI_THREADS * EG);
     int local_tile = 0;
     uint32_t satm = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
-      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, TW, STH);
+    TileWalker tw_;
+    tw_.init(blockIdx.x, grid, num_n_tiles, tiles_x, tiles_y);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile, tw_.next()) {
+      const TileCoord t = tw_.coord(block_n, TW, STH);
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (local_tile >> 1) & 1;
       // bias / PReLU slopes of the tile's N range: staged once when the layer has a single N tile (per-tile global

@@ -74,6 +74,61 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int num_n_tiles, int 
   return t;
 }
 
+// Division-free walk over the tiles blockIdx.x, blockIdx.x + grid, ... of a conv3x3 layer (one N group): the stride
+// `grid` is decomposed ONCE into mixed-radix digits (N tile, tile column, tile row, image) and added with carries per
+// step.  decode_tile costs four integer divisions (~110 SASS instructions with long dependent chains) per tile and warp;
+// on the small-N layers the epilogue warps that execute it are what the MMA issuers wait for (ncu: issuer warps stalled
+// on the accumulator-empty barrier, profiles/r02_base_conv_32_16_summary.txt).
+struct TileWalker {
+  int nt, tx, ty, b;          // current digits
+  int s_nt, s_tx, s_ty, s_b;  // digits of the stride
+  int num_n_tiles, tiles_x, tiles_y;
+  __device__ __forceinline__ void init(int tile, int stride, int num_n_tiles_, int tiles_x_, int tiles_y_) {
+    num_n_tiles = num_n_tiles_, tiles_x = tiles_x_, tiles_y = tiles_y_;
+    int m = tile / num_n_tiles;
+    nt = tile - m * num_n_tiles;
+    int q = m / tiles_x;
+    tx = m - q * tiles_x;
+    b = q / tiles_y;
+    ty = q - b * tiles_y;
+    m = stride / num_n_tiles;
+    s_nt = stride - m * num_n_tiles;
+    q = m / tiles_x;
+    s_tx = m - q * tiles_x;
+    s_b = q / tiles_y;
+    s_ty = q - s_b * tiles_y;
+  }
+  __device__ __forceinline__ void next() {
+    nt += s_nt;
+    int c = nt >= num_n_tiles ? 1 : 0;
+    nt -= c ? num_n_tiles : 0;
+    tx += s_tx + c;
+    c = tx >= tiles_x ? 1 : 0;
+    tx -= c ? tiles_x : 0;
+    ty += s_ty + c;
+    c = ty >= tiles_y ? 1 : 0;
+    ty -= c ? tiles_y : 0;
+    b += s_b + c;
+  }
+  __device__ __forceinline__ TileCoord coord(int block_n, int tile_w, int tile_h) const {
+    TileCoord t;
+    t.b = b, t.y0 = ty * tile_h, t.x0 = tx * tile_w, t.grp = 0, t.n0 = nt * block_n;
+    return t;
+  }
+  // with N groups (the four phases of the transposed conv): nt = grp * n_tiles_per_group + n tile
+  __device__ __forceinline__ TileCoord coord_groups(int block_n, int n_tiles_per_group, int tile_w, int tile_h) const {
+    TileCoord t;
+    t.b = b, t.y0 = ty * tile_h, t.x0 = tx * tile_w;
+    if (n_tiles_per_group == 1) {
+      t.grp = nt, t.n0 = 0;
+    } else {
+      t.grp = nt / n_tiles_per_group;
+      t.n0 = (nt - t.grp * n_tiles_per_group) * block_n;
+    }
+    return t;
+  }
+};
+
 template <bool kBf16>
 __device__ __forceinline__ float cvt_lo(uint32_t v) {
   return kBf16 ? bf16_lo(v) : f16_lo(v);

@@ -125,8 +125,10 @@ igemm_kernel(const __grid_constant__ KParams p) {
     int stage = 0;
     uint32_t phase = 0;
     const int pa0 = p.pair_a[0], pa1 = p.pair_a[1], pa2 = p.pair_a[2];
-    for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
-      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
+    TileWalker tw_;
+    tw_.init(blockIdx.x, grid, num_n_tiles, tiles_x, tiles_y);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, tw_.next()) {
+      const TileCoord t = tw_.coord_groups(block_n, n_tiles_per_group, STW, TILE_H);
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int pa = pair == 0 ? pa0 : pair == 1 ? pa1 : pa2;
         const CUtensorMap* tmA = pa ? &p.tmA1 : &p.tmA0;
@@ -168,8 +170,10 @@ igemm_kernel(const __grid_constant__ KParams p) {
     const uint32_t w_bytes = static_cast<uint32_t>(block_n * 128);
     const int wg = p.wgroups;
     const int pw0 = p.pair_w[0] * wg, pw1 = p.pair_w[1] * wg, pw2 = p.pair_w[2] * wg;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += grid) {
-      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
+    TileWalker tw_;
+    tw_.init(blockIdx.x, grid, num_n_tiles, tiles_x, tiles_y);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, tw_.next()) {
+      const TileCoord t = tw_.coord_groups(block_n, n_tiles_per_group, STW, TILE_H);
       for (int pair = 0; pair < n_pairs; ++pair) {
         const int wbase = pair == 0 ? pw0 : pair == 1 ? pw1 : pw2;
 #pragma unroll
@@ -259,8 +263,10 @@ igemm_kernel(const __grid_constant__ KParams p) {
     if (one_n_tile) stage_bias_slope(epi_bias, epi_slope, bias, slope, 0, block_n, cout, et, EPI_THREADS * EG);
     int local_tile = 0;
     uint32_t satm = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile) {
-      const TileCoord t = decode_tile(tile, num_n_tiles, n_tiles_per_group, block_n, tiles_x, tiles_y, STW, TILE_H);
+    TileWalker tw_;
+    tw_.init(blockIdx.x, grid, num_n_tiles, tiles_x, tiles_y);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++local_tile, tw_.next()) {
+      const TileCoord t = tw_.coord_groups(block_n, n_tiles_per_group, STW, TILE_H);
       const int acc = local_tile & 1;
       const uint32_t acc_phase = (local_tile >> 1) & 1;
       // bias / slopes depend on the tile's N offset only (not on the transposed conv's phase): staged once when every
