@@ -58,6 +58,9 @@ a.wpacked, a.bias, a.slope = wp.data_ptr(), bias.data_ptr(), slope.data_ptr()
 a.out_kind = _lib.OUT_NHWC16
 a.out[0] = out.data_ptr()
 a.out_ctot, a.out_coff = out_ctot, out_coff
+import os
+a.m_tiles = int(os.environ.get("M_TILES", "0"))
+a.block_n = int(os.environ.get("BLOCK_N", "0"))
 if res:
     a.res[0] = x.data_ptr()
     a.res_ctot = ctot

@@ -501,6 +501,9 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
     const int64_t tiles2 = slab ? static_cast<int64_t>(p.B) * cdiv(p.W, tw1) * cdiv(p.H, 2 * th1) * p.num_n_tiles
                                 : static_cast<int64_t>(p.B) * cdiv(p.W, 2 * tw1) * cdiv(p.H, th1) * p.num_n_tiles;
     mt = (block_n <= 128 && tiles2 >= 2 * sms) ? 2 : 1;
+    // transposed conv (short K = Cin, epilogue-bound): one accumulator per W tile, drained by two epilogue groups,
+    // measured 7-15 % faster than MT = 2 at every width (profiles/r02_up_conv_variants.txt)
+    if (a.mode == B200DN_MODE_UP2X2) mt = 1;
   }
   p.mt = mt;
   const int stw = slab ? tw1 : tw1 * mt, sth = slab ? th1 * mt : th1;   // super-tile extent
