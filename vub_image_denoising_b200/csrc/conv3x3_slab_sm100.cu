@@ -82,7 +82,7 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bars + B_TFULL + a * 8, MT);
-      mbar_init(bars + B_TEMPTY + a * 8, EPI_THREADS * EG);
+      mbar_init(bars + B_TEMPTY + a * 8, (EPI_THREADS / 32) * EG);   // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
@@ -325,7 +325,8 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
           tmem_ld_wait();
           if (rel != 0) {
             tc_fence_before();
-            mbar_arrive(rel);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rel);
           }
           if (valid) {
             const int64_t sp = static_cast<int64_t>(y) * W + x;

@@ -245,11 +245,14 @@ __device__ __forceinline__ void epilogue_subtile(const EpiArgs& e, uint32_t tadd
     tmem_ld_wait();
     if (release_bar != 0 && c0 + 16 >= block_n) {
       tc_fence_before();
-      if (cluster_rel) {   // CTA pair: the barrier lives in the leader CTA; one remote arrive per warp
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(release_bar);
-      } else {
-        mbar_arrive(release_bar);
+      // one arrive per WARP (the barrier counts warps): 128-256 per-thread arrives on one shared-memory word serialise
+      // and sit on the path that hands the accumulator stage back to the MMA issuers
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) {
+        if (cluster_rel)
+          mbar_arrive_cluster(release_bar);   // CTA pair: the barrier lives in the leader CTA
+        else
+          mbar_arrive(release_bar);
       }
     }
     if (!valid) continue;
@@ -354,11 +357,12 @@ __device__ __forceinline__ void epilogue_subtile_staged(const EpiArgs& e, uint32
       tmem_ld_wait();
       if (release_bar != 0 && c0 + 64 >= block_n && q4 == 3) {
         tc_fence_before();
-        if (cluster_rel) {
-          __syncwarp();
-          if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(release_bar);
-        } else {
-          mbar_arrive(release_bar);
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+          if (cluster_rel)
+            mbar_arrive_cluster(release_bar);
+          else
+            mbar_arrive(release_bar);
         }
       }
       float v[16];

@@ -91,7 +91,7 @@ igemm_kernel(const __grid_constant__ KParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bars + 128 + a * 8, MT);           // accumulators full: one commit per issuer
-      mbar_init(bars + 144 + a * 8, EPI_THREADS * EG);  // accumulators drained (every epilogue thread arrives)
+      mbar_init(bars + 144 + a * 8, (EPI_THREADS / 32) * EG);  // accumulators drained (one arrive per epilogue warp)
     }
     mbar_fence_init();
   }
