@@ -194,14 +194,14 @@ int b200dn_pack_dense_block_weights(const float* w0, const float* w1, const floa
                                     int channels, int prec, void* packed, void* stream);
 int b200dn_dense_block_prepare(const b200dn_dense_block_args* args, b200dn_igemm_prepared** out);
 
-/* ---- input block conv_1 (Cin = 3 or 4), CUDA cores, fp32 math ---------------
- * x: fp32 NCHW [Bx,3,H,W]; image b of the output reads x[b % Bx].
+/* ---- input block conv_1 (Cin = img_channels [+ 1]), CUDA cores, fp32 math ------
+ * x: fp32 NCHW [Bx,img_channels,H,W] (3 = RGB, 1 = grayscale); image b of the output reads x[b % Bx].
  * t: optional timestep plane source; element (b,y,x) = t[b*t_sb + y*t_sh + x*t_sw]
- *    (strides in elements, 0 = broadcast).  NULL -> 3-channel network.
- * w: OIHW fp32 [cout, 3|4, 3, 3].  Output: NHWC 16-bit planes, channels [0,cout).
+ *    (strides in elements, 0 = broadcast).  NULL -> no timestep channel.
+ * w: OIHW fp32 [cout, img_channels (+1), 3, 3].  Output: NHWC 16-bit planes, channels [0,cout).
  * sat_flag: optional fp16 saturation watch, as in b200dn_igemm_args.
  */
-int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_sb, int64_t t_sh, int64_t t_sw,
+int b200dn_conv_in(const float* x, int Bx, int img_channels, const float* t, int64_t t_sb, int64_t t_sh, int64_t t_sw,
                    int B, int H, int W, int cout,
                    const float* w, const float* bias, const float* slope,
                    int prec, void* out0, void* out1, int out_ctot, int32_t* sat_flag, void* stream);

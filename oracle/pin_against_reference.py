@@ -103,6 +103,17 @@ def main() -> None:
     assert torch.equal(orc.rdunet_forward(big_t.state_dict(), x64, torch.tensor([0.5]).view(1, 1, 1, 1), "unet."), y64)
     gold.update(D_x=x64.numpy(), D_y=y64.numpy())
 
+    # ---- case E: grayscale RDUNet(channels=1, base_filters=16) — the reference ctor takes `channels` for both ends
+    #      (UNet/RDUNet_model.py:117-155); evaluate_model.calculate_ssim(use_rgb=False) is its metric path
+    torch.manual_seed(17)
+    gray = RDUNet(channels=1, base_filters=16).eval()
+    sd_g = gray.state_dict()
+    gold["E_digest"] = np.frombuffer(bytes.fromhex(sd_digest(sd_g)), dtype=np.uint8)
+    xg = torch.rand(2, 1, 16, 24, generator=g) * 2 - 1
+    yg = gray(xg)
+    assert torch.equal(orc.rdunet_forward(sd_g, xg), yg)
+    gold.update(E_x=xg.numpy(), E_y=yg.numpy())
+
     # FLOP count of the oracle's formula vs the survey's hook measurement
     assert abs(orc.conv_flops(32) / 1e9 - 96.26) < 0.01, orc.conv_flops(32) / 1e9
     assert abs(orc.conv_flops(128) / 1e9 - 1537.43) < 0.01, orc.conv_flops(128) / 1e9

@@ -34,6 +34,32 @@ def test_rdunet_golden(golden, precision, max_abs, built_lib):
                 assert float((got - ref).abs().max()) <= max_abs
 
 
+@pytest.mark.parametrize("precision,max_abs", [("bf16", None), ("fp16", None), ("bf16x3", 1e-4)])
+def test_rdunet_grayscale_golden(golden, precision, max_abs, built_lib):
+    """RDUNet(channels=1): the reference ctor takes `channels` for both ends (UNet/RDUNet_model.py:117-155); golden
+    vector from the real reference, same seeded init."""
+    torch.manual_seed(17)
+    net = b2.RDUNet(channels=1, base_filters=16)
+    assert sd_digest(net.state_dict()) == bytes(golden["E_digest"]).hex(), "init differs from the reference ctor"
+    net = net.to(DEV).eval()
+    net.precision = precision
+    x = torch.from_numpy(golden["E_x"]).to(DEV)
+    ref = torch.from_numpy(golden["E_y"]).to(DEV)
+    with torch.no_grad():
+        got = net(x)
+        assert got.shape == ref.shape == (2, 1, 16, 24)
+        _check_bar(got, ref, what=f"grayscale RDUNet(16) {precision}")
+        if max_abs is not None:
+            assert float((got - ref).abs().max()) <= max_abs
+        assert torch.equal(net(x), got)                      # graph replay path
+        with pytest.raises(RuntimeError, match="channels"):
+            net(torch.zeros(1, 3, 16, 16, device=DEV))
+    # grayscale metric path of evaluate_model.calculate_ssim(use_rgb=False)
+    from oracle import metrics_oracle as mo
+    s = b2.metrics.calculate_ssim(got[0, 0], ref[0, 0], 1.0, use_rgb=False)
+    assert s == pytest.approx(mo.structural_similarity(got[0, 0].cpu().numpy(), ref[0, 0].cpu().numpy(), data_range=1.0), abs=1e-5)
+
+
 @pytest.mark.parametrize("precision,max_abs", [("bf16", None), ("bf16x2", None), ("bf16x3", 1e-4)])
 def test_rdunet_t_golden(golden, precision, max_abs, built_lib):
     torch.manual_seed(11)
@@ -328,9 +354,9 @@ def test_unsupported_configurations_raise(built_lib):
     with torch.no_grad():
         with pytest.raises(RuntimeError, match="multiple of 16"):
             b2.RDUNet(base_filters=24).to(DEV).eval()(torch.zeros(1, 3, 16, 16, device=DEV))
-        gray = b2.RDUNet(channels=1, base_filters=16).to(DEV).eval()
-        with pytest.raises(RuntimeError, match="3-channel"):
-            gray(torch.zeros(1, 1, 16, 16, device=DEV))
+        two = b2.RDUNet(channels=2, base_filters=16).to(DEV).eval()
+        with pytest.raises(RuntimeError, match="RGB .3-channel. and grayscale"):
+            two(torch.zeros(1, 2, 16, 16, device=DEV))
         net = b2.RDUNet(base_filters=16).to(DEV).eval()
         net.precision = "int8"
         with pytest.raises(RuntimeError, match="unknown precision"):

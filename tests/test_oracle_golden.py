@@ -56,6 +56,17 @@ def test_oracle_rdunet_matches_reference_outputs(golden):
             assert torch.equal(y, _t(golden[f"A_y{k}"]))
 
 
+def test_oracle_grayscale_matches_reference_outputs(golden):
+    """RDUNet(channels=1): seeded init == the reference ctor's, oracle == the reference's output."""
+    torch.manual_seed(17)
+    net = b2.RDUNet(channels=1, base_filters=16)
+    sd = net.state_dict()
+    assert sd_digest(sd) == bytes(golden["E_digest"]).hex()
+    assert sd["input_block.conv_1.weight"].shape == (16, 1, 3, 3) and sd["output_block.conv_2.weight"].shape == (1, 16, 3, 3)
+    with torch.no_grad():
+        assert torch.equal(orc.rdunet_forward(sd, _t(golden["E_x"])), _t(golden["E_y"]))
+
+
 def test_oracle_rdunet_t_matches_reference_outputs(golden):
     torch.manual_seed(11)
     sd = b2.RDUNet_T(base_filters=16).state_dict()

@@ -57,7 +57,7 @@ L = b2._lib.lib()
 
 def conv_in():
     hi, lo = I0.ptrs()
-    L.b200dn_conv_in(xin.data_ptr(), 64, None, 0, 0, 0, 64, 256, 256, 128, plan.in_w, plan.in_b, plan.in_s, plan.prec, hi, lo, I0.ctot,
+    L.b200dn_conv_in(xin.data_ptr(), 64, 3, None, 0, 0, 0, 64, 256, 256, 128, plan.in_w, plan.in_b, plan.in_s, plan.prec, hi, lo, I0.ctot,
                      None, torch.cuda.current_stream().cuda_stream)
 
 

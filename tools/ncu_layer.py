@@ -61,6 +61,8 @@ a.out_ctot, a.out_coff = out_ctot, out_coff
 import os
 a.m_tiles = int(os.environ.get("M_TILES", "0"))
 a.block_n = int(os.environ.get("BLOCK_N", "0"))
+a.impl = int(os.environ.get("IMPL", "0"))
+a.max_ctas = int(os.environ.get("MAX_CTAS", "0"))
 if res:
     a.res[0] = x.data_ptr()
     a.res_ctot = ctot

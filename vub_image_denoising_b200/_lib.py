@@ -124,7 +124,7 @@ def lib() -> C.CDLL:
     L.b200dn_dense_block_weight_bytes.argtypes = [i32]
     L.b200dn_pack_dense_block_weights.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     L.b200dn_dense_block_prepare.argtypes = [C.POINTER(DenseBlockArgs), C.POINTER(vp)]
-    L.b200dn_conv_in.argtypes = [vp, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp]
+    L.b200dn_conv_in.argtypes = [vp, i32, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp]
     L.b200dn_sampler_step.argtypes = [vp, vp, vp, vp, f32, f32, f32, f32, vp, i64, vp]
     L.b200dn_lerp.argtypes = [vp, vp, f32, f32, vp, i64, vp]
     L.b200dn_psnr_sse.argtypes = [vp, vp, i64, i64, vp, vp, i64, vp]

@@ -51,7 +51,8 @@ __device__ __forceinline__ void store_group(const float (&acc)[8], const float* 
 // shared memory (2 x LDS.128 per k and group); sharing them between two pixels halves the shared-memory reads per FMA
 // (the one-pixel version issued one LDS.128 per 4 FFMA and ran at a third of the FP32 rate), and the two pixels share
 // 8 of their 12 input rows x columns.
-template <int CIN>
+// CIMG = channels of the image (3 RGB, 1 grayscale); HAS_T = the RDUNet_T timestep plane as an extra input channel
+template <int CIMG, bool HAS_T>
 __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restrict__ x, int Bx,
                                                             const float* __restrict__ t, int64_t t_sb, int64_t t_sh,
                                                             int64_t t_sw, int H, int W, int cout,
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
                                                             const float* __restrict__ slope, int prec,
                                                             uint16_t* __restrict__ out0, uint16_t* __restrict__ out1,
                                                             int out_ctot, int* __restrict__ sat_flag) {
+  constexpr int CIN = CIMG + (HAS_T ? 1 : 0);
   extern __shared__ float w_s[];  // [CIN*9][cout], then bias[cout], slope[cout]
   constexpr int K = CIN * 9;
   float* b_s = w_s + K * cout;
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
   const int b = blockIdx.z;
   const int xx = blockIdx.x * PX + threadIdx.x;
   const int64_t hw = static_cast<int64_t>(H) * W;
-  const float* xb = x + static_cast<int64_t>(b % Bx) * 3 * hw;
+  const float* xb = x + static_cast<int64_t>(b % Bx) * CIMG * hw;
   const bool is_bf16 = (prec != B200DN_PREC_FP16) && (prec != B200DN_PREC_FP16X2);
   if (xx >= W) return;
   uint32_t satm = 0;
@@ -95,8 +97,8 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
         const bool in = (yy >= 0) && (yy < H) && (xc >= 0) && (xc < W);
         const int64_t sp = static_cast<int64_t>(yy) * W + xc;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) v[ci][r][kx] = in ? __ldg(xb + ci * hw + sp) : 0.f;
-        if (CIN == 4) v[3][r][kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
+        for (int ci = 0; ci < CIMG; ++ci) v[ci][r][kx] = in ? __ldg(xb + ci * hw + sp) : 0.f;
+        if (HAS_T) v[CIMG][r][kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
       }
     }
     const int64_t pix = (static_cast<int64_t>(b) * H + y) * W + xx;
@@ -153,12 +155,31 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
 }  // namespace
 }  // namespace b200dn
 
-extern "C" int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_sb, int64_t t_sh, int64_t t_sw, int B,
-                              int H, int W, int cout, const float* w, const float* bias, const float* slope, int prec,
-                              void* out0, void* out1, int out_ctot, int32_t* sat_flag, void* stream) {
+namespace b200dn {
+namespace {
+template <int CIMG, bool HAS_T>
+int launch_conv_in(dim3 grid, dim3 block, size_t smem, cudaStream_t s, const float* x, int Bx, const float* t, int64_t t_sb,
+                   int64_t t_sh, int64_t t_sw, int H, int W, int cout, const float* w, const float* bias, const float* slope,
+                   int prec, uint16_t* o0, uint16_t* o1, int out_ctot, int* sat_flag) {
+  if (smem > 48 * 1024)
+    B200DN_CUDA(cudaFuncSetAttribute(conv_in_kernel<CIMG, HAS_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_in_kernel<CIMG, HAS_T><<<grid, block, smem, s>>>(x, Bx, t, t_sb, t_sh, t_sw, H, W, cout, w, bias, slope, prec, o0, o1,
+                                                         out_ctot, sat_flag);
+  B200DN_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+}  // namespace b200dn
+
+extern "C" int b200dn_conv_in(const float* x, int Bx, int img_channels, const float* t, int64_t t_sb, int64_t t_sh,
+                              int64_t t_sw, int B, int H, int W, int cout, const float* w, const float* bias,
+                              const float* slope, int prec, void* out0, void* out1, int out_ctot, int32_t* sat_flag,
+                              void* stream) {
   using namespace b200dn;
   B200DN_CHECK_ARG(x && w && bias && slope && out0, "conv_in: null pointer");
   B200DN_CHECK_ARG(B > 0 && Bx > 0 && H > 0 && W > 0, "conv_in: non-positive dims");
+  B200DN_CHECK_ARG(img_channels == 3 || img_channels == 1, "conv_in: image channels must be 3 (RGB) or 1 (grayscale), got %d",
+                   img_channels);
   B200DN_CHECK_ARG(cout > 0 && cout % 8 == 0, "conv_in: cout %d must be a multiple of 8", cout);
   B200DN_CHECK_ARG(out_ctot % 8 == 0 && out_ctot >= cout, "conv_in: out_ctot %d invalid", out_ctot);
   B200DN_CHECK_ARG(prec >= 0 && prec <= 4, "conv_in: bad prec %d", prec);
@@ -166,24 +187,16 @@ extern "C" int b200dn_conv_in(const float* x, int Bx, const float* t, int64_t t_
   B200DN_CHECK_ARG(!two || out1, "conv_in: prec %d needs the lo output plane", prec);
   B200DN_CHECK_ARG(B <= 65535 && H <= 65535 * 2 * ROWS * PASSES, "conv_in: B/H exceed the grid limit");
   if (int rc = require_sm100()) return rc;
-  const int cin = t ? 4 : 3;
+  const int cin = img_channels + (t ? 1 : 0);
   const size_t smem = (static_cast<size_t>(cin) * 9 + 2) * cout * sizeof(float);
   B200DN_CHECK_ARG(smem <= 160 * 1024, "conv_in: cout %d too large", cout);
   dim3 block(PX, ROWS), grid(cdiv(W, PX), cdiv(H, 2 * ROWS * PASSES), B);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint16_t* o0 = static_cast<uint16_t*>(out0);
   uint16_t* o1 = two ? static_cast<uint16_t*>(out1) : nullptr;
-  if (cin == 4) {
-    if (smem > 48 * 1024)
-      B200DN_CUDA(cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_in_kernel<4><<<grid, block, smem, s>>>(x, Bx, t, t_sb, t_sh, t_sw, H, W, cout, w, bias, slope, prec, o0, o1,
-                                                out_ctot, sat_flag);
-  } else {
-    if (smem > 48 * 1024)
-      B200DN_CUDA(cudaFuncSetAttribute(conv_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_in_kernel<3><<<grid, block, smem, s>>>(x, Bx, nullptr, 0, 0, 0, H, W, cout, w, bias, slope, prec, o0, o1,
-                                                out_ctot, sat_flag);
-  }
-  B200DN_CUDA(cudaGetLastError());
-  return 0;
+  if (img_channels == 3)
+    return t ? launch_conv_in<3, true>(grid, block, smem, s, x, Bx, t, t_sb, t_sh, t_sw, H, W, cout, w, bias, slope, prec, o0, o1, out_ctot, sat_flag)
+             : launch_conv_in<3, false>(grid, block, smem, s, x, Bx, nullptr, 0, 0, 0, H, W, cout, w, bias, slope, prec, o0, o1, out_ctot, sat_flag);
+  return t ? launch_conv_in<1, true>(grid, block, smem, s, x, Bx, t, t_sb, t_sh, t_sw, H, W, cout, w, bias, slope, prec, o0, o1, out_ctot, sat_flag)
+           : launch_conv_in<1, false>(grid, block, smem, s, x, Bx, nullptr, 0, 0, 0, H, W, cout, w, bias, slope, prec, o0, o1, out_ctot, sat_flag);
 }

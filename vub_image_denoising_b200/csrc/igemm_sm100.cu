@@ -541,8 +541,13 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
     const int64_t w_all = static_cast<int64_t>(p.n_wplanes) * p.n_cblk * 9 * block_n * 128;
     // small layers: keep the whole packed weight set resident in shared memory (single N tile only; cout < 64: such
     // layers never use the staged epilogue, so its 16 KB belong to the resident weights) next to >= 2 slabs
-    p.wres = (impl != 3 && p.num_n_tiles == 1 && block_n < 64 && w_all <= SLAB_WRES_BYTES - 2 * p.slab_bytes &&
-              wres_enabled()) ? 1 : 0;
+    // N = 32..48 layers with K >= 9 * 64 on a full grid go to the CTA-pair kernel instead (measured 7-14 % faster than
+    // resident weights at cin 64..128 / 256x256 and 128x128, slower at cin 32; profiles/r02_n32_pairs_vs_wres.txt)
+    const int pair_tiles0 = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
+    const bool small_n_pairs = a.impl == 0 && cta2_mode() >= 1 && block_n >= 32 && block_n < 64 && a.cin >= 64 &&
+                               pair_tiles0 >= sms / 2;
+    p.wres = (impl != 3 && !small_n_pairs && p.num_n_tiles == 1 && block_n < 64 &&
+              w_all <= SLAB_WRES_BYTES - 2 * p.slab_bytes && wres_enabled()) ? 1 : 0;
     // CTA pairs (cta_group::2, conv3x3_slab2_sm100.cu): each SM keeps half of every W tile.  Explicit impl 3, or by
     // default for the streaming-weight layers (N >= 64): when every SM pair gets at least one pair tile, and also
     // when the grid is under-filled anyway (batch 1-2, deep levels) — there each CTA is paced by the latency of its
@@ -550,7 +555,7 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
     const int pair_tiles = cdiv(p.num_m_tiles, 2) * p.num_n_tiles;
     const bool pairs_fit = pair_tiles >= sms / 2 || (cta2_mode() == 1 && p.num_tiles < sms && p.num_m_tiles >= 2);
     p.cta2 = (!p.wres && block_n >= 32 &&
-              (impl == 3 || (a.impl == 0 && cta2_mode() >= 1 && block_n >= 64 && pairs_fit))) ? 1 : 0;
+              (impl == 3 || small_n_pairs || (a.impl == 0 && cta2_mode() >= 1 && block_n >= 64 && pairs_fit))) ? 1 : 0;
     if (p.cta2) p.num_tiles = pair_tiles;
     p.w_taps = 1;
     if (p.wres) {

@@ -6,11 +6,14 @@
 // detrend = 'constant' (each segment's mean removed), one-sided density scaling (x2 except DC / Nyquist,
 // 1 / (fs * sum(w^2)) = 1/96), mean over segments; float32 input -> complex64 transform -> float32 spectrum.
 //
-// One block = 128 threads = one 256-point complex radix-2 Stockham FFT in shared memory per step, carrying TWO real
-// segments (z = a + i b; A[k] = (Z[k] + conj Z[N-k]) / 2, B[k] = (Z[k] - conj Z[N-k]) / 2i).  A block walks a strided
-// share of the segment pairs of one signal and writes one partial spectrum; a second kernel adds the partials in a
-// fixed order (bit-reproducible, no atomics).  Bytes: each sample is read twice (50 % overlap, the second time from
-// L1/L2) and 129 floats are written per signal, so the kernel is bound by the FFT's shared-memory traffic, not by HBM.
+// One HALF-WARP = one 256-point complex FFT carrying TWO real segments (z = a + i b; A[k] = (Z[k] + conj Z[N-k]) / 2,
+// B[k] = (Z[k] - conj Z[N-k]) / 2i), as 16 x 16 Cooley-Tukey with the data in registers: thread t holds z[16 n1 + t],
+// does a 16-point radix-2 DIF over n1 (compile-time twiddles), multiplies by W256^(t k1), transposes through a
+// per-half-warp shared-memory tile (__syncwarp only) and does the second 16-point FFT over n2; thread k1 then holds the
+// bins k1 + 16 k2 and fetches the mirrored bins from lane (16 - k1) & 15 with shuffles.  A block (8 half-warps) walks a
+// strided share of one signal's segment pairs, adds its half-warps' spectra in a fixed order and writes one partial; a
+// second kernel adds the partials in a fixed order (bit-reproducible, no atomics).
+// The first version ran one block-wide radix-2 Stockham FFT per pair (eight __syncthreads per transform): 0.38 TB/s.
 #include "common.cuh"
 
 namespace b200dn {
@@ -20,85 +23,139 @@ namespace {
 constexpr int NSEG = 256;            // nperseg = nfft
 constexpr int HOP = 128;             // nperseg - noverlap
 constexpr int NBINS = NSEG / 2 + 1;  // 129
-constexpr int WT = 128;              // threads per block
+constexpr int WT = 128;              // threads per block = 8 half-warps
+constexpr int HW_PER_BLOCK = WT / 16;
 constexpr int MAX_BLOCKS_PER_SIGNAL = 64;
+constexpr int TP = 17;               // transpose tile pitch (float2), conflict-free for 8-byte accesses of a half-warp
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-__device__ __forceinline__ float block_sum128(float v, float* red, int slot) {
+// W16^j = exp(-2 pi i j / 16), j = 0..7
+__device__ __forceinline__ float2 w16(int j) {
+  constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r = 0.70710678118654752f;
+  switch (j) {
+    case 0: return make_float2(1.f, 0.f);
+    case 1: return make_float2(c1, -s1);
+    case 2: return make_float2(r, -r);
+    case 3: return make_float2(s1, -c1);
+    case 4: return make_float2(0.f, -1.f);
+    case 5: return make_float2(-s1, -c1);
+    case 6: return make_float2(-r, -r);
+    default: return make_float2(-c1, -s1);
+  }
+}
+__device__ __forceinline__ constexpr int bitrev4(int i) { return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3); }
+
+// in-register 16-point radix-2 DIF: afterwards a[i] = X[bitrev4(i)]
+__device__ __forceinline__ void fft16(float2 (&a)[16]) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if ((threadIdx.x & 31) == 0) red[slot * 4 + (threadIdx.x >> 5)] = v;
-  __syncthreads();
-  return (red[slot * 4] + red[slot * 4 + 1]) + (red[slot * 4 + 2] + red[slot * 4 + 3]);
+  for (int h = 8; h >= 1; h >>= 1) {
+#pragma unroll
+    for (int b = 0; b < 16; b += 2 * h) {
+#pragma unroll
+      for (int j = 0; j < h; ++j) {
+        const float2 u = a[b + j], v = a[b + j + h];
+        a[b + j] = cadd(u, v);
+        const float2 d = csub(u, v);
+        a[b + j + h] = (j == 0) ? d : cmul(d, w16(j * (8 / h)));
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(WT) welch_kernel(const float* __restrict__ x, int64_t n, int64_t nseg,
                                                    float* __restrict__ partial) {
-  __shared__ float2 buf[2][NSEG];
-  __shared__ float2 tw[NSEG / 2];
+  __shared__ float2 tile[HW_PER_BLOCK][16 * TP];
+  __shared__ float2 tw[NSEG];
   __shared__ float win[NSEG];
-  __shared__ float red[16];
+  __shared__ float accs[HW_PER_BLOCK][NBINS + 3];
   const int tid = threadIdx.x;
   const float* sig = x + static_cast<int64_t>(blockIdx.y) * n;
-  {
+  for (int i = tid; i < NSEG; i += WT) {
     float s, c;
-    sincospif(-static_cast<float>(tid) / 128.0f, &s, &c);   // exp(-2 pi i tid / 256)
-    tw[tid] = make_float2(c, s);
-    win[tid] = 0.5f - 0.5f * cospif(static_cast<float>(tid) / 128.0f);
-    win[tid + 128] = 0.5f - 0.5f * cospif(static_cast<float>(tid + 128) / 128.0f);
+    sincospif(-static_cast<float>(i) / 128.0f, &s, &c);   // exp(-2 pi i k / 256)
+    tw[i] = make_float2(c, s);
+    win[i] = 0.5f - 0.5f * cospif(static_cast<float>(i) / 128.0f);   // periodic Hann
   }
   __syncthreads();
-  float acc = 0.f, acc_nyq = 0.f;   // bin tid; thread 0 also carries bin 128
+  const int hw = tid >> 4, t = tid & 15;
+  const unsigned hmask = 0xffffu << (tid & 16);           // this half-warp's lanes
+  float2* my = tile[hw];
+  float acc[8];
+#pragma unroll
+  for (int k2 = 0; k2 < 8; ++k2) acc[k2] = 0.f;
+  float acc_nyq = 0.f;
   const int64_t npairs = (nseg + 1) / 2;
-  int flip = 0;
-  for (int64_t pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * HW_PER_BLOCK;
+  for (int64_t pair = static_cast<int64_t>(blockIdx.x) * HW_PER_BLOCK + hw; pair < npairs; pair += stride) {
     const int64_t s0 = 2 * pair;
     const bool has_b = s0 + 1 < nseg;
     const float* pa = sig + s0 * HOP;
-    // segment b = samples [HOP, HOP + 256) of the same window: the pair spans 384 consecutive samples
-    const float a0 = pa[tid], a1 = pa[tid + 128];
-    const float b0 = a1, b1 = has_b ? pa[tid + 256] : 0.f;
-    const float mean_a = block_sum128(a0 + a1, red, flip) * (1.0f / NSEG);
-    const float mean_b = block_sum128(has_b ? b0 + b1 : 0.f, red, flip + 2) * (1.0f / NSEG);
-    float2* in = buf[0];
-    float2* out = buf[1];
-    in[tid] = make_float2((a0 - mean_a) * win[tid], has_b ? (b0 - mean_b) * win[tid] : 0.f);
-    in[tid + 128] = make_float2((a1 - mean_a) * win[tid + 128], has_b ? (b1 - mean_b) * win[tid + 128] : 0.f);
-    __syncthreads();
+    // segment a = samples [0, 256), segment b = [128, 384) of the same window; thread t takes samples 16 n1 + t
+    float va[16], vb[16];
+    float sa = 0.f, sb = 0.f;
 #pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const int ns = 1 << s;
-      const int k = tid & (ns - 1);
-      const float2 u = in[tid];
-      const float2 v = cmul(in[tid + 128], tw[k * (128 >> s)]);
-      const int o = ((tid - k) << 1) + k;
-      out[o] = make_float2(u.x + v.x, u.y + v.y);
-      out[o + ns] = make_float2(u.x - v.x, u.y - v.y);
-      __syncthreads();
-      float2* t = in;
-      in = out;
-      out = t;
+    for (int n1 = 0; n1 < 16; ++n1) {
+      va[n1] = pa[16 * n1 + t];
+      vb[n1] = has_b ? pa[HOP + 16 * n1 + t] : 0.f;
+      sa += va[n1];
+      sb += vb[n1];
     }
-    // 8 stages: the result is back in buf[0] (= in)
-    {
-      const float2 zk = in[tid];
-      const float2 zn = in[(NSEG - tid) & (NSEG - 1)];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      sa += __shfl_xor_sync(hmask, sa, o);
+      sb += __shfl_xor_sync(hmask, sb, o);
+    }
+    const float mean_a = sa * (1.0f / NSEG), mean_b = sb * (1.0f / NSEG);
+    float2 a[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const float w = win[16 * n1 + t];
+      a[n1] = make_float2((va[n1] - mean_a) * w, has_b ? (vb[n1] - mean_b) * w : 0.f);
+    }
+    fft16(a);                                   // over n1: a[bitrev4(k1)] = Y_t[k1]
+    __syncwarp(hmask);                          // the previous pair's reads of the tile are done
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) my[t * TP + k1] = cmul(a[bitrev4(k1)], tw[(t * k1) & (NSEG - 1)]);
+    __syncwarp(hmask);
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) a[n2] = my[n2 * TP + t];       // thread t = k1 now
+    fft16(a);                                   // over n2: a[bitrev4(k2)] = Z[k1 + 16 k2]
+    // power of both real segments at k = k1 + 16 k2, k2 = 0..7; mirrored bin 256 - k lives in lane (16 - k1) & 15
+    const int partner = ((16 - t) & 15) | (tid & 16);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; ++k2) {
+      const float2 zk = a[bitrev4(k2)];
+      const float2 own = a[bitrev4((16 - k2) & 15)];                // lane 0: 256 - 16 k2 = 16 (16 - k2)
+      const float2 give = a[bitrev4(15 - k2)];                      // what this lane holds for its partner
+      float2 zn;
+      zn.x = __shfl_sync(hmask, give.x, partner);
+      zn.y = __shfl_sync(hmask, give.y, partner);
+      if (t == 0) zn = own;
       // A = (zk + conj zn) / 2, B = (zk - conj zn) / (2i)
       const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
       const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
-      acc += (ar * ar + ai * ai) + (br * br + bi * bi);
-      if (tid == 0) {
-        const float2 zq = in[128];   // Nyquist: A = Re, B = Im
-        acc_nyq += zq.x * zq.x + zq.y * zq.y;
-      }
+      acc[k2] += (ar * ar + ai * ai) + (br * br + bi * bi);
     }
-    flip ^= 1;   // alternate the reduction scratch so the next pair's writes cannot race this pair's reads
-    __syncthreads();
+    if (t == 0) {
+      const float2 zq = a[bitrev4(8)];   // Nyquist bin 128: A = Re, B = Im
+      acc_nyq += zq.x * zq.x + zq.y * zq.y;
+    }
   }
+  // fixed-order sum of the block's eight half-warp spectra -> one partial per block
+#pragma unroll
+  for (int k2 = 0; k2 < 8; ++k2) accs[hw][t + 16 * k2] = acc[k2];
+  if (t == 0) accs[hw][128] = acc_nyq;
+  __syncthreads();
   float* p = partial + (static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x) * NBINS;
-  p[tid] = acc;
-  if (tid == 0) p[128] = acc_nyq;
+  for (int k = tid; k < NBINS; k += WT) {
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < HW_PER_BLOCK; ++h) s += accs[h][k];
+    p[k] = s;
+  }
 }
 
 // pxx[sig][k] = scale_k / nseg * sum over blocks of partial[sig][block][k], fixed order
@@ -115,7 +172,8 @@ __global__ void welch_finish_kernel(const float* __restrict__ partial, int n_blo
 int blocks_per_signal(int64_t n_signals, int64_t nseg, int sms) {
   const int64_t npairs = (nseg + 1) / 2;
   int64_t want = cdiv64(static_cast<int64_t>(sms) * 16, n_signals);   // ~16 resident blocks (of 128 threads) per SM over all signals
-  if (want > npairs) want = npairs;
+  const int64_t max_useful = cdiv64(npairs, HW_PER_BLOCK);     // a block runs eight transforms at a time
+  if (want > max_useful) want = max_useful;
   if (want > MAX_BLOCKS_PER_SIGNAL) want = MAX_BLOCKS_PER_SIGNAL;
   if (want < 1) want = 1;
   return static_cast<int>(want);

@@ -146,7 +146,7 @@ def conv_in(x: torch.Tensor, t: Optional[torch.Tensor], weight: torch.Tensor, bi
     _cuda(x, t, weight, bias, slope, out_hi, out_lo)
     Bx, _, H, W = x.shape
     with torch.cuda.device(x.device):
-        rc = _lib.lib().b200dn_conv_in(x.data_ptr(), Bx, _ptr(t), 1 if t is not None else 0, 0, 0, batch, H, W,
+        rc = _lib.lib().b200dn_conv_in(x.data_ptr(), Bx, x.shape[1], _ptr(t), 1 if t is not None else 0, 0, 0, batch, H, W,
                                        weight.shape[0], weight.data_ptr(), bias.data_ptr(), slope.data_ptr(), prec,
                                        out_hi.data_ptr(), _ptr(out_lo), out_hi.shape[-1], None, _stream(x))
     _lib.check(rc, "conv_in")

@@ -209,7 +209,7 @@ class _RDUNetBase(nn.Module):
 
 
 class RDUNet(_RDUNetBase):
-    """Residual-dense U-Net, 3-channel in/out (reference: UNet/RDUNet_model.py:117-186)."""
+    """Residual-dense U-Net, `channels` in and out: 3 (RGB) or 1 (grayscale) (reference: UNet/RDUNet_model.py:117-186)."""
 
     def __init__(self, channels: int = 3, base_filters: int = 64):
         super().__init__()
@@ -273,9 +273,9 @@ class ForwardPlan:
         F = net.base_filters
         if F % 16:
             raise RuntimeError(f"base_filters={F}: the B200 kernels need a multiple of 16")
-        if net._img_channels != 3 or net._out_channels != 3:
-            raise RuntimeError("the B200 path implements the reference's 3-channel (RGB) networks; "
-                               f"got channels={net._img_channels} in / {net._out_channels} out")
+        if net._img_channels not in (1, 3) or net._out_channels != net._img_channels:
+            raise RuntimeError("the B200 path implements the reference's RGB (3-channel) and grayscale (1-channel) "
+                               f"networks; got channels={net._img_channels} in / {net._out_channels} out")
         self.lib = _lib.lib()
         self.prec = _lib.PREC_NAMES[precision]
         self.precision = precision
@@ -284,6 +284,7 @@ class ForwardPlan:
         self.two = self.prec in _lib.TWO_PLANE_PRECS
         self.with_t = net._in_channels == net._img_channels + 1
         self.out_channels = net._out_channels
+        self.img_channels = net._img_channels
         self.signature = None
         self._keep = []          # tensors referenced by raw pointer from the arg blocks
         self._handles = None     # b200dn_igemm_prepared* per launch (encoded tensor maps + launch geometry)
@@ -565,7 +566,7 @@ class ForwardPlan:
             t_ptr, t_strides = None, (0, 0, 0)
         I0 = self.bufs["I0"]
         hi, lo = I0.ptrs()
-        rc = lib.b200dn_conv_in(x.data_ptr(), bx, t_ptr, t_strides[0], t_strides[1], t_strides[2],
+        rc = lib.b200dn_conv_in(x.data_ptr(), bx, self.img_channels, t_ptr, t_strides[0], t_strides[1], t_strides[2],
                                 self.B, self.H, self.W, self.F, self.in_w, self.in_b, self.in_s, self.prec,
                                 hi, lo, I0.ctot, self.sat_flag.data_ptr() if self.sat_flag is not None else None, stream)
         _lib.check(rc, "conv_in")
