@@ -237,7 +237,10 @@ def test_conv_in(B, bx, H, W, cout, with_t, prec, built_lib):
     xin = x.double().cpu().repeat(B // bx, 1, 1, 1)
     if with_t:
         xin = torch.cat([xin, t.double().cpu().view(B, 1, 1, 1).expand(B, 1, H, W)], 1)
-    ref = F.prelu(F.conv2d(xin, w.double().cpu(), bias.double().cpu(), padding=1), slope.double().cpu())
+    # single-plane modes run the tensor-core ingest: weights rounded to the 16-bit type like every other layer's, the fp32
+    # image carried as hi + lo planes; the two-plane (validation) modes keep the fp32 CUDA-core kernel
+    we = w if two_planes(prec) else effective_weight(w, prec)
+    ref = F.prelu(F.conv2d(xin, we.double().cpu(), bias.double().cpu(), padding=1), slope.double().cpu())
     _check_slice(out_hi, out_lo, prec, 0, cout, ref, "conv_in")
 
 

@@ -3,7 +3,9 @@
 // reference concatenates at diffusion_denoising/Unet/Unet_model.py:135-136), writes NHWC 16-bit planes.
 // K = 27 or 36 is far too small for the tensor pipe and the layer is bandwidth-bound (AI ~ 26 FLOP/B),
 // so this runs on CUDA cores in fp32.
-#include "common.cuh"
+#include "igemm_common.cuh"
+
+#include <stdlib.h>
 
 namespace b200dn {
 
@@ -156,6 +158,239 @@ __global__ void __launch_bounds__(PX * ROWS) conv_in_kernel(const float* __restr
 }  // namespace b200dn
 
 namespace b200dn {
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core ingest (single-plane bf16 / fp16 modes).  The CUDA-core kernel above is fp32-FMA bound: 2.4 GFMA for
+// RDUNet_T(32) at B = 32 = 145 us = 3.3 % of a sampler step, 0.83 ms of the RDUNet(128) step (ncu launch lists,
+// profiles/r02_*_launches.csv).  Here the K = 27 / 36 (ci, ky, kx) patch of every pixel is gathered once into a
+// K-major 128-byte-swizzled A tile in shared memory as TWO 16-bit planes (hi + lo: the fp32 image keeps ~22 bits, so
+// the ingest stays exact in its input), the conv weights sit resident as one 16-bit plane (the same rounding every
+// other layer's weights get) and the layer is 2 x ceil(K / 16) tcgen05.mma per 128 pixels.
+// Warp roles (416 threads): 0-3 and 9-12 = two epilogue groups (one half of the accumulator columns each: with one
+// group the 128-channel ingest ran 2 % slower), 4-7 and 13-16 = two gather groups (thread = pixel of an 8 x 16 tile; group
+// g fills A stage g for the CTA's even / odd tiles — the gather, ~300 instructions per pixel behind its image loads,
+// is what paces a tile), 8 = TMEM allocator + MMA issuer.
+namespace ingest_tc {
+using namespace igemm;
+constexpr int TW_ = SLAB_TILE_W, TH_ = SLAB_TILE_H;           // 8 x 16 pixels = 128 accumulator rows
+constexpr int A_PLANE_BYTES = 128 * 128;                      // [128 px][64 k] 16-bit, 128-byte swizzled rows
+constexpr int STAGES = 2;
+constexpr int MAX_COUT = 256;
+constexpr uint32_t OFF_W = 0;                                  // [cout_pad][64 k]: up to 32 KB
+constexpr uint32_t OFF_A = MAX_COUT * 128;                     // STAGES x {hi, lo}
+constexpr uint32_t OFF_BAR = OFF_A + STAGES * 2 * A_PLANE_BYTES;
+constexpr uint32_t OFF_EPI = OFF_BAR + 128;                    // bias[256], slope[256]
+constexpr uint32_t SMEM = 1024 + OFF_EPI + 2 * MAX_COUT * 4;
+constexpr uint32_t B_AFULL = 0, B_AEMPTY = 16, B_TFULL = 32, B_TEMPTY = 48, B_TMEMPTR = 64;
+constexpr int THREADS = 544;   // 17 warps: 0-3 / 9-12 epilogue groups (column halves), 4-7 / 13-16 gather groups, 8 issuer
+
+template <int CIMG, bool HAS_T, bool kBf16>
+__global__ void __launch_bounds__(THREADS, 1) conv_in_tc_kernel(const float* __restrict__ x, int Bx, const float* __restrict__ t,
+                                                                int64_t t_sb, int64_t t_sh, int64_t t_sw, int B, int H, int W,
+                                                                int cout, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, const float* __restrict__ slope,
+                                                                uint16_t* __restrict__ out0, int out_ctot, int* sat_flag) {
+  constexpr int CIN = CIMG + (HAS_T ? 1 : 0);
+  constexpr int K = CIN * 9;
+  constexpr int NK16 = (K + 15) / 16;                          // 2 (K = 9, 18, 27) or 3 (K = 36)
+  constexpr int NCHUNK = NK16 * 2;                             // 16-byte chunks (8 k) written per row and plane
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = smem_u32(smem_raw);
+  const uint32_t sb = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* sg = smem_raw + (sb - raw_u32);
+  const uint32_t bars = sb + OFF_BAR;
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sg + OFF_BAR + B_TMEMPTR);
+  float* epi_bias = reinterpret_cast<float*>(sg + OFF_EPI);
+  float* epi_slope = epi_bias + MAX_COUT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int block_n = (cout + 15) & ~15;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(STAGES * block_n)) tmem_cols <<= 1;
+  const int n_groups = (block_n % 32 == 0) ? 2 : 1;           // epilogue groups that have columns to drain
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(bars + B_AFULL + s * 8, 4);     // one arrive per gather warp
+        mbar_init(bars + B_AEMPTY + s * 8, 1);    // tcgen05.commit
+        mbar_init(bars + B_TFULL + s * 8, 1);     // tcgen05.commit
+        mbar_init(bars + B_TEMPTY + s * 8, 4 * n_groups);    // one arrive per active epilogue warp
+      }
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_ptr_s), tmem_cols);
+    tmem_relinquish();
+  }
+  // resident weights: [n][k = ci*9 + ky*3 + kx] 16-bit, K-major 128-byte swizzled rows, zero padded (generic-proxy stores)
+  for (int i = threadIdx.x; i < block_n * 8; i += THREADS) {
+    const int n = i >> 3, chunk = i & 7;
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k0 = chunk * 8 + 2 * q;
+      const float a = (n < cout && k0 < K) ? __ldg(w + n * K + k0) : 0.f;
+      const float c = (n < cout && k0 + 1 < K) ? __ldg(w + n * K + k0 + 1) : 0.f;
+      v[q] = kBf16 ? pack_bf16x2(a, c) : pack_f16x2(a, c);
+    }
+    *reinterpret_cast<uint4*>(sg + OFF_W + n * 128 + ((chunk ^ (n & 7)) << 4)) = make_uint4(v[0], v[1], v[2], v[3]);
+  }
+  for (int i = threadIdx.x; i < block_n; i += THREADS) {
+    epi_bias[i] = i < cout ? __ldg(bias + i) : 0.f;
+    epi_slope[i] = i < cout ? __ldg(slope + i) : 1.f;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+  griddep_launch_dependents();
+
+  const int tiles_x = (W + TW_ - 1) / TW_, tiles_y = (H + TH_ - 1) / TH_;
+  const int num_tiles = B * tiles_x * tiles_y, grid = gridDim.x;
+  const int64_t hw = static_cast<int64_t>(H) * W;
+
+  if ((warp >= 4 && warp < 8) || warp >= 13) {
+    // ===================================================== gather: thread = pixel, im2col row -> A tile (hi, lo planes)
+    griddep_wait();      // x may be the previous kernel's output (the sampler's x_t)
+    const int gg = warp >= 13 ? 1 : 0;                         // gather group = A stage = parity of the CTA-local tile index
+    const int pxl = ((warp - 4) & 3) * 32 + lane;              // warps 4-7 -> 0..3, warps 13-16 -> (9..12) & 3 = 1,2,3,0
+    const int th = pxl >> 3, tw = pxl & 7;
+    const uint32_t row_off = static_cast<uint32_t>(pxl) * 128u, swz = static_cast<uint32_t>(pxl & 7);
+    TileWalker wk;
+    wk.init(blockIdx.x + gg * grid, 2 * grid, 1, tiles_x, tiles_y);
+    int it = gg;
+    for (int tile = blockIdx.x + gg * grid; tile < num_tiles; tile += 2 * grid, wk.next(), it += 2) {
+      const int st = gg;
+      const uint32_t ph = static_cast<uint32_t>((it >> 1) & 1);
+      const int b = wk.b, y = wk.ty * TH_ + th, xx = wk.tx * TW_ + tw;
+      const float* xb = x + static_cast<int64_t>(b % Bx) * CIMG * hw;
+      float v[NCHUNK * 8];
+#pragma unroll
+      for (int k = K; k < NCHUNK * 8; ++k) v[k] = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = y + ky - 1, xc = xx + kx - 1;
+          const bool in = (yy >= 0) && (yy < H) && (xc >= 0) && (xc < W);
+          const int64_t sp = static_cast<int64_t>(yy) * W + xc;
+#pragma unroll
+          for (int ci = 0; ci < CIMG; ++ci) v[ci * 9 + ky * 3 + kx] = in ? __ldg(xb + ci * hw + sp) : 0.f;
+          if (HAS_T) v[CIMG * 9 + ky * 3 + kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
+        }
+      }
+      mbar_wait(bars + B_AEMPTY + st * 8, ph ^ 1u);       // the MMAs that read this stage have retired
+      uint8_t* a_hi = sg + OFF_A + (st * 2) * A_PLANE_BYTES + row_off;
+      uint8_t* a_lo = a_hi + A_PLANE_BYTES;
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float a = v[c * 8 + 2 * q], d = v[c * 8 + 2 * q + 1];
+          hi[q] = kBf16 ? pack_bf16x2(a, d) : pack_f16x2(a, d);
+          const float ra = a - (kBf16 ? bf16_lo(hi[q]) : f16_lo(hi[q])), rd = d - (kBf16 ? bf16_hi(hi[q]) : f16_hi(hi[q]));
+          lo[q] = kBf16 ? pack_bf16x2(ra, rd) : pack_f16x2(ra, rd);
+        }
+        const uint32_t off = (static_cast<uint32_t>(c) ^ swz) << 4;
+        *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + B_AFULL + st * 8);
+    }
+  } else if (warp == 8) {
+    // ===================================================== MMA issuer: D = A_lo W + A_hi W, 2 x NK16 UMMAs per tile
+    const uint32_t idesc = make_idesc_f16(kBf16 ? 1u : 0u, static_cast<uint32_t>(block_n));
+    const uint64_t bdesc = make_sw128_desc(sb + OFF_W, 1024);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, ++it) {
+      const int st = it & 1;
+      const uint32_t ph = static_cast<uint32_t>((it >> 1) & 1);
+      mbar_wait(bars + B_TEMPTY + st * 8, ph ^ 1u);       // accumulator stage drained
+      mbar_wait(bars + B_AFULL + st * 8, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d = tmem_base + static_cast<uint32_t>(st * block_n);
+        const uint64_t a_hi = make_sw128_desc(sb + OFF_A + (st * 2) * A_PLANE_BYTES, 1024);
+        const uint64_t a_lo = make_sw128_desc(sb + OFF_A + (st * 2 + 1) * A_PLANE_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < NK16; ++k) umma_f16(d, a_lo + 2 * k, bdesc + 2 * k, idesc, k == 0 ? 0u : 1u);   // small term first
+#pragma unroll
+        for (int k = 0; k < NK16; ++k) umma_f16(d, a_hi + 2 * k, bdesc + 2 * k, idesc, 1u);
+        umma_commit(bars + B_AEMPTY + st * 8);
+        umma_commit(bars + B_TFULL + st * 8);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4 || (warp >= 9 && n_groups == 2)) {
+    // ===================================================== epilogue: bias + PReLU -> 16-bit NHWC channels [0, cout)
+    griddep_wait();      // WAR: the previous kernel may still read the buffer this layer writes
+    const int grp = warp >= 9 ? 1 : 0;
+    const int we = warp & 3;                                    // TMEM lane quarter this warp may read
+    const int ncols = block_n / n_groups, col0 = grp * ncols;
+    const int row = we * 32 + lane;
+    const int th = row >> 3, tw = row & 7;
+    EpiArgs ea;
+    ea.out0 = out0, ea.out1 = nullptr, ea.res0 = nullptr, ea.res1 = nullptr;
+    ea.out_ctot = out_ctot, ea.out_coff = 0, ea.res_ctot = 0, ea.cout = cout;
+    ea.out_kind = B200DN_OUT_NHWC16, ea.is_bf16 = kBf16 ? 1 : 0;
+    ea.out_nchw = nullptr, ea.res_nchw = nullptr, ea.res_bmod = 1, ea.H = H, ea.W = W;
+    ea.sat_flag = kBf16 ? nullptr : sat_flag;
+    uint32_t satm = 0;
+    TileWalker wk;
+    wk.init(blockIdx.x, grid, 1, tiles_x, tiles_y);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += grid, wk.next(), ++it) {
+      const int st = it & 1;
+      const uint32_t ph = static_cast<uint32_t>((it >> 1) & 1);
+      const int b = wk.b, y = wk.ty * TH_ + th, xx = wk.tx * TW_ + tw;
+      const bool valid = (y < H) && (xx < W);
+      const int64_t pix = (static_cast<int64_t>(b) * H + y) * W + xx;
+      mbar_wait(bars + B_TFULL + st * 8, ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>(st * block_n + col0);
+      epilogue_subtile(ea, taddr, ncols, epi_bias + col0, epi_slope + col0, valid, b, y, xx, pix, pix, col0,
+                       bars + B_TEMPTY + st * 8, satm);
+    }
+    sat_report(ea.sat_flag, satm);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+template <int CIMG, bool HAS_T>
+int launch(int grid, cudaStream_t s, const float* x, int Bx, const float* t, int64_t t_sb, int64_t t_sh, int64_t t_sw, int B,
+           int H, int W, int cout, const float* w, const float* bias, const float* slope, bool bf16, uint16_t* o0, int out_ctot,
+           int* sat_flag) {
+  static const void* const kernels[2] = {reinterpret_cast<const void*>(conv_in_tc_kernel<CIMG, HAS_T, false>),
+                                         reinterpret_cast<const void*>(conv_in_tc_kernel<CIMG, HAS_T, true>)};
+  static SmemOptIn opt_in;
+  if (int rc = ensure_max_dyn_smem(opt_in, kernels, 2, SMEM, "cudaFuncSetAttribute(conv_in_tc_kernel, smem)")) return rc;
+  if (bf16)
+    conv_in_tc_kernel<CIMG, HAS_T, true><<<grid, THREADS, SMEM, s>>>(x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, o0,
+                                                                      out_ctot, sat_flag);
+  else
+    conv_in_tc_kernel<CIMG, HAS_T, false><<<grid, THREADS, SMEM, s>>>(x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, o0,
+                                                                       out_ctot, sat_flag);
+  B200DN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+bool enabled() {
+  static int on = [] {
+    const char* e = getenv("B200DN_CONV_IN_TC");
+    return e ? atoi(e) : 1;
+  }();
+  return on != 0;
+}
+}  // namespace ingest_tc
+
 namespace {
 template <int CIMG, bool HAS_T>
 int launch_conv_in(dim3 grid, dim3 block, size_t smem, cudaStream_t s, const float* x, int Bx, const float* t, int64_t t_sb,
@@ -194,6 +429,20 @@ extern "C" int b200dn_conv_in(const float* x, int Bx, int img_channels, const fl
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint16_t* o0 = static_cast<uint16_t*>(out0);
   uint16_t* o1 = two ? static_cast<uint16_t*>(out1) : nullptr;
+  const bool single = prec == B200DN_PREC_BF16 || prec == B200DN_PREC_FP16;
+  if (single && ingest_tc::enabled() && cout % 8 == 0 && cout <= ingest_tc::MAX_COUT) {
+    // tensor-core ingest (single-plane modes): persistent grid, one CTA per SM
+    const int tiles = B * cdiv(W, ingest_tc::TW_) * cdiv(H, ingest_tc::TH_);
+    int sms = device_sm_count();
+    if (sms <= 0) return B200DN_E_CUDA;
+    const int g = tiles < sms ? tiles : sms;
+    const bool bf = prec == B200DN_PREC_BF16;
+    if (img_channels == 3)
+      return t ? ingest_tc::launch<3, true>(g, s, x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag)
+               : ingest_tc::launch<3, false>(g, s, x, Bx, nullptr, 0, 0, 0, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag);
+    return t ? ingest_tc::launch<1, true>(g, s, x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag)
+             : ingest_tc::launch<1, false>(g, s, x, Bx, nullptr, 0, 0, 0, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag);
+  }
   if (img_channels == 3)
     return t ? launch_conv_in<3, true>(grid, block, smem, s, x, Bx, t, t_sb, t_sh, t_sw, H, W, cout, w, bias, slope, prec, o0, o1, out_ctot, sat_flag)
              : launch_conv_in<3, false>(grid, block, smem, s, x, Bx, nullptr, 0, 0, 0, H, W, cout, w, bias, slope, prec, o0, o1, out_ctot, sat_flag);
