@@ -114,6 +114,23 @@ def main() -> None:
     assert torch.equal(orc.rdunet_forward(sd_g, xg), yg)
     gold.update(E_x=xg.numpy(), E_y=yg.numpy())
 
+    # ---- case F: widths off the kernels' channel tiling (the reference ctor takes any base_filters, growth = F // 2):
+    #      RDUNet(base_filters=24) and RDUNet_T(base_filters=10)
+    torch.manual_seed(19)
+    n24 = RDUNet(base_filters=24).eval()
+    gold["F_digest24"] = np.frombuffer(bytes.fromhex(sd_digest(n24.state_dict())), dtype=np.uint8)
+    x24 = torch.rand(1, 3, 16, 24, generator=g) * 2 - 1
+    y24 = n24(x24)
+    assert torch.equal(orc.rdunet_forward(n24.state_dict(), x24), y24)
+    torch.manual_seed(23)
+    n10 = RDUNet_T(base_filters=10).eval()
+    gold["F_digest10"] = np.frombuffer(bytes.fromhex(sd_digest(n10.state_dict())), dtype=np.uint8)
+    x10 = torch.rand(2, 3, 16, 16, generator=g) * 2 - 1
+    t10 = torch.tensor([0.15, 0.7]).view(2, 1, 1, 1)
+    y10 = n10(x10, t10)
+    assert torch.equal(orc.rdunet_forward(n10.state_dict(), x10, t10), y10)
+    gold.update(F_x24=x24.numpy(), F_y24=y24.numpy(), F_x10=x10.numpy(), F_t10=t10.numpy(), F_y10=y10.numpy())
+
     # FLOP count of the oracle's formula vs the survey's hook measurement
     assert abs(orc.conv_flops(32) / 1e9 - 96.26) < 0.01, orc.conv_flops(32) / 1e9
     assert abs(orc.conv_flops(128) / 1e9 - 1537.43) < 0.01, orc.conv_flops(128) / 1e9

@@ -60,6 +60,40 @@ def test_rdunet_grayscale_golden(golden, precision, max_abs, built_lib):
     assert s == pytest.approx(mo.structural_similarity(got[0, 0].cpu().numpy(), ref[0, 0].cpu().numpy(), data_range=1.0), abs=1e-5)
 
 
+@pytest.mark.parametrize("precision,max_abs", [("bf16", None), ("fp16", None), ("bf16x3", 1e-4)])
+def test_widths_off_the_channel_tiling_golden(golden, precision, max_abs, built_lib):
+    """base_filters = 24 and 10 (the reference ctor takes any width, UNet/RDUNet_model.py:117-155): the plan runs the
+    zero-padded 32- / 16-filter embedding; golden vectors from the real reference, same seeded init."""
+    with torch.no_grad():
+        torch.manual_seed(19)
+        net = b2.RDUNet(base_filters=24)
+        assert sd_digest(net.state_dict()) == bytes(golden["F_digest24"]).hex()
+        net = net.to(DEV).eval()
+        net.precision = precision
+        x, ref = torch.from_numpy(golden["F_x24"]).to(DEV), torch.from_numpy(golden["F_y24"]).to(DEV)
+        got = net(x)
+        _check_bar(got, ref, what=f"RDUNet(24) {precision}")
+        if max_abs is not None:
+            assert float((got - ref).abs().max()) <= max_abs
+        assert torch.equal(net(x), got)                      # graph replay path
+        assert len(net.state_dict()) == 207 and net.block_0_0.conv_0.weight.shape == (12, 24, 3, 3)
+        torch.manual_seed(23)
+        net = b2.RDUNet_T(base_filters=10)
+        assert sd_digest(net.state_dict()) == bytes(golden["F_digest10"]).hex()
+        net = net.to(DEV).eval()
+        net.precision = precision
+        x, t = torch.from_numpy(golden["F_x10"]).to(DEV), torch.from_numpy(golden["F_t10"]).to(DEV)
+        ref = torch.from_numpy(golden["F_y10"]).to(DEV)
+        got = net(x, t)
+        _check_bar(got, ref, what=f"RDUNet_T(10) {precision}")
+        if max_abs is not None:
+            assert float((got - ref).abs().max()) <= max_abs
+        # a parameter update is picked up (the padded copy is rebuilt with the plan)
+        net.output_block.conv_2.weight.zero_()
+        net.output_block.conv_2.bias.zero_()
+        assert torch.equal(net(x, t), x)                     # PReLU(0) + global residual
+
+
 @pytest.mark.parametrize("precision,max_abs", [("bf16", None), ("bf16x2", None), ("bf16x3", 1e-4)])
 def test_rdunet_t_golden(golden, precision, max_abs, built_lib):
     torch.manual_seed(11)
@@ -352,8 +386,6 @@ def test_ragged_shapes_and_widths_vs_oracle(base_filters, shape, built_lib):
 
 def test_unsupported_configurations_raise(built_lib):
     with torch.no_grad():
-        with pytest.raises(RuntimeError, match="multiple of 16"):
-            b2.RDUNet(base_filters=24).to(DEV).eval()(torch.zeros(1, 3, 16, 16, device=DEV))
         two = b2.RDUNet(channels=2, base_filters=16).to(DEV).eval()
         with pytest.raises(RuntimeError, match="RGB .3-channel. and grayscale"):
             two(torch.zeros(1, 2, 16, 16, device=DEV))

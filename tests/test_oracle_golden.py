@@ -67,6 +67,31 @@ def test_oracle_grayscale_matches_reference_outputs(golden):
         assert torch.equal(orc.rdunet_forward(sd, _t(golden["E_x"])), _t(golden["E_y"]))
 
 
+def test_oracle_and_zero_padded_embedding_at_widths_off_the_channel_tiling(golden):
+    """base_filters = 24 / 10 (growth = F // 2): seeded init == the reference ctor's, oracle == the reference's outputs,
+    and the zero-padded network the launch plan is built from (rdunet._zero_padded_network) computes the same
+    function — checked with the oracle on the CPU, so the embedding is pinned without a GPU."""
+    from vub_image_denoising_b200.rdunet import _zero_padded_network
+    with torch.no_grad():
+        torch.manual_seed(19)
+        n24 = b2.RDUNet(base_filters=24)
+        assert sd_digest(n24.state_dict()) == bytes(golden["F_digest24"]).hex()
+        x, y = _t(golden["F_x24"]), _t(golden["F_y24"])
+        assert torch.equal(orc.rdunet_forward(n24.state_dict(), x), y)
+        wide = _zero_padded_network(n24, 32)
+        assert wide.base_filters == 32 and wide.block_0_0.conv_1.weight.shape == (16, 48, 3, 3)
+        assert float((orc.rdunet_forward(wide.state_dict(), x) - y).abs().max()) < 2e-6
+        torch.manual_seed(23)
+        n10 = b2.RDUNet_T(base_filters=10)
+        assert sd_digest(n10.state_dict()) == bytes(golden["F_digest10"]).hex()
+        x, t, y = _t(golden["F_x10"]), _t(golden["F_t10"]), _t(golden["F_y10"])
+        assert torch.equal(orc.rdunet_forward(n10.state_dict(), x, t), y)
+        wide = _zero_padded_network(n10, 16)
+        assert float((orc.rdunet_forward(wide.state_dict(), x, t) - y).abs().max()) < 2e-6
+        # the embedding leaves the caller's module alone
+        assert n10.base_filters == 10 and n10.block_1_0.conv_0.weight.shape == (10, 20, 3, 3)
+
+
 def test_oracle_rdunet_t_matches_reference_outputs(golden):
     torch.manual_seed(11)
     sd = b2.RDUNet_T(base_filters=16).state_dict()

@@ -110,7 +110,7 @@ class _RDUNetBase(nn.Module):
     _in_channels: int   # channels seen by input_block.conv_1
     _img_channels = 3   # channels of the image tensor handed to forward()
 
-    def _build(self, in_channels: int, out_channels: int, base_filters: int) -> None:
+    def _build(self, in_channels: int, out_channels: int, base_filters: int, init: bool = True) -> None:
         f = [base_filters * (1 << l) for l in range(4)]
         self.base_filters = base_filters
         self._in_channels = in_channels
@@ -137,7 +137,8 @@ class _RDUNetBase(nn.Module):
         self.block_0_2 = _dense_block(f[0])
         self.block_0_3 = _dense_block(f[0])
         self.output_block = _io_block(f[0], f[0], out_channels)
-        self.apply(init_weights())
+        if init:
+            self.apply(init_weights())
         # private caches (not parameters / buffers -> invisible to state_dict)
         self._plans: dict = {}
         self.precision = DEFAULT_PREC
@@ -242,6 +243,88 @@ class RDUNet_T(_RDUNetBase):
         return torch.ops.b200dn.rdunet_forward(x, t, plan.plan_id)
 
 
+# --------------------------------------------------------------------------- widths the kernels do not tile
+def _copy_blocks(dst: torch.Tensor, src: torch.Tensor, out_segs, in_segs, transposed: bool = False) -> None:
+    """dst[physical] = src[logical] block by block; segs are [(logical length, physical length), ...] along the
+    output / input channel axes (Conv2d weight [out, in, kh, kw]; ConvTranspose2d weight [in, out, kh, kw])."""
+    if transposed:
+        out_segs, in_segs = in_segs, out_segs      # dim 0 is the input axis
+    o_l = o_p = 0
+    for ol, op in out_segs:
+        i_l = i_p = 0
+        for il, ip in in_segs:
+            dst[o_p:o_p + ol, i_p:i_p + il] = src[o_l:o_l + ol, i_l:i_l + il]
+            i_l, i_p = i_l + il, i_p + ip
+        o_l, o_p = o_l + ol, o_p + op
+
+
+def _copy_vec(dst: torch.Tensor, src: torch.Tensor, segs) -> None:
+    l = p = 0
+    for sl, sp in segs:
+        dst[p:p + sl] = src[l:l + sl]
+        l, p = l + sl, p + sp
+
+
+@torch.no_grad()
+def _zero_padded_network(net: "_RDUNetBase", Fp: int) -> "_RDUNetBase":
+    """The same function as `net`, embedded in a network of base_filters Fp > F whose extra channels are exactly zero.
+
+    The reference ctor takes any `base_filters` (UNet/RDUNet_model.py:117-155; growth = filters // 2); the kernels tile
+    channels in groups of 8, i.e. want F % 16 == 0.  Every logical channel segment ([x | o0 | o1 | o2] of a
+    DenoisingBlock, [skip | upsampled] of an UpsampleBlock) keeps its place at the FRONT of the wider physical segment;
+    the padded rows / columns of every weight and the padded biases are 0, so a padded channel is PReLU(0) = 0 in
+    every layer, contributes nothing downstream and the residual adds 0 + 0.  Used only while a plan is built."""
+    F = net.base_filters
+    dev = next(net.parameters()).device
+    with torch.device(dev):
+        wide = net.__class__.__new__(net.__class__)
+        nn.Module.__init__(wide)
+        wide._img_channels = net._img_channels
+        wide._build(net._in_channels, net._out_channels, Fp, init=False)
+    for p in wide.parameters():
+        p.zero_()
+
+    def conv(dst, src, out_segs, in_segs, transposed=False):
+        _copy_blocks(dst.weight, src.weight.to(torch.float32), out_segs, in_segs, transposed)
+        _copy_vec(dst.bias, src.bias.to(torch.float32), out_segs)
+
+    def actv(dst, src, segs):
+        _copy_vec(dst.weight, src.weight.to(torch.float32), segs)
+
+    cin, cout = net._in_channels, net._out_channels
+    f0 = [(F, Fp)]
+    conv(wide.input_block.conv_1, net.input_block.conv_1, f0, [(cin, cin)])
+    conv(wide.input_block.conv_2, net.input_block.conv_2, f0, f0)
+    actv(wide.input_block.actv_1, net.input_block.actv_1, f0)
+    actv(wide.input_block.actv_2, net.input_block.actv_2, f0)
+    conv(wide.output_block.conv_1, net.output_block.conv_1, f0, f0)
+    conv(wide.output_block.conv_2, net.output_block.conv_2, [(cout, cout)], f0)
+    actv(wide.output_block.actv_1, net.output_block.actv_1, f0)
+    actv(wide.output_block.actv_2, net.output_block.actv_2, [(cout, cout)])
+    for l in range(4):
+        c, cp = F << l, Fp << l
+        x, o = [(c, cp)], [(c // 2, cp // 2)]
+        for j in range(4):
+            name = f"block_{l}_{j}"
+            if not hasattr(net, name):
+                continue
+            src, dst = getattr(net, name), getattr(wide, name)
+            for k in range(4):
+                out = o if k < 3 else x
+                conv(getattr(dst, f"conv_{k}"), getattr(src, f"conv_{k}"), out, x + o * k)
+                actv(getattr(dst, f"actv_{k}"), getattr(src, f"actv_{k}"), out)
+        if l < 3:
+            deep = [(2 * c, 2 * cp)]
+            conv(getattr(wide, f"down_{l}").conv, getattr(net, f"down_{l}").conv, deep, x)
+            actv(getattr(wide, f"down_{l}").actv, getattr(net, f"down_{l}").actv, deep)
+            up_s, up_d = getattr(net, f"up_{l}"), getattr(wide, f"up_{l}")
+            conv(up_d.conv_t, up_s.conv_t, deep, deep, transposed=True)
+            actv(up_d.actv_t, up_s.actv_t, deep)
+            conv(up_d.conv, up_s.conv, x, x + deep)        # torch.cat([skip, upsampled]) (RDUNet_model.py:69)
+            actv(up_d.actv, up_s.actv, x)
+    return wide.eval()
+
+
 # --------------------------------------------------------------------------- the launch plan
 class _Act:
     """An NHWC 16-bit activation buffer: one (hi) or two (hi, lo) planes of [B, H, W, ctot]."""
@@ -271,16 +354,20 @@ class ForwardPlan:
         if precision not in _lib.PREC_NAMES:
             raise RuntimeError(f"unknown precision {precision!r}; choose from {sorted(_lib.PREC_NAMES)}")
         F = net.base_filters
-        if F % 16:
-            raise RuntimeError(f"base_filters={F}: the B200 kernels need a multiple of 16")
+        if F < 2:
+            raise RuntimeError(f"base_filters={F}: a DenoisingBlock needs filters // 2 >= 1 inner channels")
         if net._img_channels not in (1, 3) or net._out_channels != net._img_channels:
             raise RuntimeError("the B200 path implements the reference's RGB (3-channel) and grayscale (1-channel) "
                                f"networks; got channels={net._img_channels} in / {net._out_channels} out")
         self.lib = _lib.lib()
         self.prec = _lib.PREC_NAMES[precision]
         self.precision = precision
-        self.B, self.H, self.W, self.F = B, H, W, F
         self.device = next(net.parameters()).device
+        self.logical_filters = F
+        if F % 16:      # widths the kernels do not tile run zero-padded to the next multiple of 16 (exact, see above)
+            F = -(-F // 16) * 16
+            net = _zero_padded_network(net, F)
+        self.B, self.H, self.W, self.F = B, H, W, F
         self.two = self.prec in _lib.TWO_PLANE_PRECS
         self.with_t = net._in_channels == net._img_channels + 1
         self.out_channels = net._out_channels
