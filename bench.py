@@ -7,7 +7,8 @@
 Metric (BASELINE.json): denoised MPix/s, RDUNet(base_filters=128) bf16 inference on batches of 64
 256x256 RGB patches, sigma cycling over {10,20,30,40,50}, PSNR/SSIM evaluated on device.
 One "step" = one batch through the hot path: device noise synthesis from the clean uint8 patches ->
-RDUNet forward (1 CUDA-core ingest conv + 68 tcgen05 implicit-GEMM launches) -> PSNR + SSIM reductions.
+RDUNet forward (1 ingest conv + the plan's tcgen05 launches: 68 convolutions, the four of a DenoisingBlock in one
+chained launch where the plan chains them) -> PSNR + SSIM reductions.
 `value` is timed with the clean batch resident in HBM; `e2e` runs the same step from pinned HOST buffers
 with the H2D copy of the patches and the D2H copy of the denoised batch + metrics inside the timed region
 (copies on two side streams, double-buffered, so they overlap the neighbouring steps' compute).
@@ -226,7 +227,8 @@ def diffusion_metrics(b2, dev, world, rank, clean_dev, peaks, barrier):
                        "hbm_ms_per_sample": t_hbm * 1e3, "hbm_gbs_achieved": DIFF_BYTES_PER_SAMPLE / t_s / 1e9,
                        "algorithmic_flops_per_sample": DIFF_FLOP_PER_SAMPLE,
                        "algorithmic_bytes_per_sample": DIFF_BYTES_PER_SAMPLE, "peak_source": peaks["source"],
-                       "traffic": None, "kernels": "40 x (conv_in + 68 tcgen05 launches) + 20 x sampler_step per sample batch, "
+                       "traffic": None, "kernels": "40 x (conv_in + 68 tcgen05 convolutions, level 0 as fused blocks, levels 1-2 as chained "
+                                                   "launches) + 20 x sampler_step per sample batch, "
                                                    "one CUDA graph; per-layer ncu captures under profiles/"}
     # (2) end to end through the public call with HOST buffers: pinned noisy batch -> H2D -> improved_sampling -> D2H
     host_in = noisy16.cpu().pin_memory()
@@ -362,7 +364,7 @@ def run_b200(args) -> None:
         barrier()
         clocks = sampler.finish()
         ms_total = e0.elapsed_time(e1)
-        # device time of the 68 igemm launches of a step, averaged over the timed steps
+        # device time of the tensor-core launches of a step, averaged over the timed steps
         igemm_last_ms = float(np.mean([a.elapsed_time(b) for a, b in ev_pairs]))
         red = acc.reduce()                                         # ONE all-reduce of (sum psnr, sum ssim, n)
         # ---------------- timed region 2: end to end from pinned host buffers
@@ -415,24 +417,26 @@ def run_b200(args) -> None:
     value = world * B * MPIX_PER_PATCH / (ms_step / 1e3)
     e2e_value = world * B * MPIX_PER_PATCH / (e2e_ms_total / args.steps / 1e3)
 
-    # roofline of the dominant kernel (igemm_kernel): algorithmic FLOPs of the 68 launches / their device time
+    # roofline of the dominant kernel family: algorithmic FLOPs of the tensor-core launches / their device time
     # 2*MAC of the 68 tensor-core convolutions of one step (SURVEY.md §8 d: F = 128 -> 1537.43 - 0.45 GFLOP per image),
     # summed from the launch plan itself
     igemm_flops = sum(info["flops"] for info in plan.layer_info)
     achieved = igemm_flops / (igemm_last_ms / 1e3) / 1e12
-    # DRAM traffic of the same 68 launches from the committed ncu pass over this command (profiles/), per launch
+    # DRAM traffic of the same launches from the committed ncu pass over this command (profiles/), per launch
     traffic = None
     summ = ROOT / "profiles" / "r02_bench_launches_summary.json"
     if not summ.exists():
         summ = ROOT / "profiles" / "r01_bench_launches_summary.json"
     if summ.exists() and F == 128 and B == 64:
         traffic = json.loads(summ.read_text())["tensor_core_kernels"]["dram_bytes_per_launch"]
-    roofline = {"bound": "tensor", "kernel": "conv3x3_slab2_kernel (cta_group::2) + conv3x3_slab_kernel + igemm_kernel "
-                                             "(68 tcgen05 launches per step)",
+    n_tc = len(plan.launches)
+    roofline = {"bound": "tensor", "kernel": "conv3x3_slab2_kernel / conv3x3_chain_kernel (cta_group::2) + conv3x3_slab_kernel + "
+                                             f"igemm_kernel ({n_tc} tcgen05 launches per step for 68 convolutions)",
                 "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops"], "traffic": traffic,
-                "traffic_note": f"dram__bytes_read+write per launch, mean over the 68 launches (ncu, profiles/{summ.name}); "
-                                "algorithmic layer-by-layer bytes are 1.83 GB per launch, so L2 already absorbs re-reads",
+                "traffic_note": f"dram__bytes_read+write per launch, mean over the tensor-core launches of one step (ncu, "
+                                f"profiles/{summ.name}); algorithmic layer-by-layer bytes are 124.6 GB per step = "
+                                f"{124.6 / n_tc:.2f} GB per launch, so L2 already absorbs re-reads",
                 "peak_source": peaks["source"],
                 "algorithmic_flops_per_step": igemm_flops, "kernel_ms_per_step": igemm_last_ms,
                 "kernel_share_of_step": igemm_last_ms / ms_step}

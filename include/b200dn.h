@@ -23,6 +23,9 @@
  *                           (UNet/RDUNet_model.py:157-186) become one C call over a prebuilt list
  *   b200dn_dense_block_prepare / b200dn_pack_dense_block_weights
  *                           DenoisingBlock as one kernel             UNet/RDUNet_model.py:95-115
+ *   b200dn_conv_chain_prepare / b200dn_conv_chain_workspace_bytes
+ *                           conv_0..conv_3 of a DenoisingBlock of any width as ONE persistent launch whose tiles
+ *                           wait on the tiles they read, not on a launch boundary   UNet/RDUNet_model.py:106-115
  *   b200dn_conv_in          InputBlock.conv_1 + actv_1, t-plane cat  UNet/RDUNet_model.py:71-81,
  *                                                                    diffusion_denoising/Unet/Unet_model.py:133-136
  *   b200dn_pack_conv_weight / b200dn_pack_convt_weight
@@ -193,6 +196,26 @@ int64_t b200dn_dense_block_weight_bytes(int channels);
 int b200dn_pack_dense_block_weights(const float* w0, const float* w1, const float* w2, const float* w3,
                                     int channels, int prec, void* packed, void* stream);
 int b200dn_dense_block_prepare(const b200dn_dense_block_args* args, b200dn_igemm_prepared** out);
+
+/* ---- 2..4 DEPENDENT 3x3 convolutions of one resolution in one persistent launch (csrc/conv3x3_chain_sm100.cu) ------
+ * layers[k] is a b200dn_igemm_args as b200dn_igemm takes it (MODE_CONV3X3, OUT_NHWC16, PREC_BF16 or PREC_FP16, all
+ * tuning knobs 0, same B/H/W/prec).  Layer k may read anything written before the launch plus the outputs of layers
+ * < k (the [x | o0 | o1 | o2] slices of a DenoisingBlock); no layer may write channels that it or an earlier layer of the
+ * chain reads as input (checked).  A tile of layer k starts as soon as the 3 x 3 neighbourhood of tiles of layer k-1
+ * is stored (per-tile counters in `workspace`), so the layers overlap and the pipelines never drain in between.
+ * Results are bit-equal to launching the layers one by one.
+ * workspace: device buffer of b200dn_conv_chain_workspace_bytes, 16-byte aligned, zero-filled ONCE by the caller and
+ * owned by this handle afterwards (counters are monotonic across launches; no reset is needed).
+ * Returns B200DN_E_UNSUP (handle NULL) when the layers do not all run on the CTA-pair kernel with one tiling, or
+ * when a layer has fewer than two rounds of tiles per SM pair (batch 1-2: nothing to overlap, measured slower than
+ * separate launches; flags = B200DN_CHAIN_FORCE builds the chain anyway) — launch them one by one then.
+ * Launch with b200dn_igemm_launch / _launch_list.  Its CTAs wait on each other: chain launches on DIFFERENT streams
+ * of one device must not overlap (env B200DN_CHAIN_COOP=1 makes the launch cooperative, which lifts this but cannot
+ * run under ncu); one launch of a handle at a time. */
+int64_t b200dn_conv_chain_workspace_bytes(const b200dn_igemm_args* layers, int n_layers);
+#define B200DN_CHAIN_FORCE 1
+int b200dn_conv_chain_prepare(const b200dn_igemm_args* layers, int n_layers, void* workspace, int flags,
+                              b200dn_igemm_prepared** out);
 
 /* ---- input block conv_1 (Cin = img_channels [+ 1]), CUDA cores, fp32 math ------
  * x: fp32 NCHW [Bx,img_channels,H,W] (3 = RGB, 1 = grayscale); image b of the output reads x[b % Bx].

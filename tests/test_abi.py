@@ -106,6 +106,15 @@ def test_no_gpu_means_error_not_fallback(built_lib):
     assert built_lib.b200dn_igemm_launch_list(None, 0, None) == -1
     assert built_lib.b200dn_igemm_rebind_nchw(None, None, None, 0) == -1
     built_lib.b200dn_igemm_release(None)          # releasing a null handle is a no-op
+    # chained launches: same contract
+    two = (_lib.IgemmArgs * 2)()
+    assert built_lib.b200dn_conv_chain_workspace_bytes(None, 2) == -1
+    two[0].B, two[0].H, two[0].W = 2, 32, 40
+    assert built_lib.b200dn_conv_chain_workspace_bytes(two, 2) >= (2 * 2 * 5 + 2) * 4      # one counter per 8 x 16 tile
+    h = ctypes.c_void_p(123)
+    assert built_lib.b200dn_conv_chain_prepare(two, 1, 16, 0, ctypes.byref(h)) == -1 and h.value is None    # 2..4 layers
+    assert built_lib.b200dn_conv_chain_prepare(two, 2, None, 0, ctypes.byref(h)) == -1                      # no workspace
+    assert built_lib.b200dn_conv_chain_prepare(None, 2, 16, 0, ctypes.byref(h)) == -1
 
 
 def test_stale_library_is_refused(built_lib, tmp_path, monkeypatch):

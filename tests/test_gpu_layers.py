@@ -324,6 +324,7 @@ def test_fused_and_per_layer_networks_agree(built_lib, monkeypatch):
     fp32 summation order -> the two forwards agree to a few 16-bit ulps of the activations."""
     import vub_image_denoising_b200 as b2
     from vub_image_denoising_b200 import rdunet
+    monkeypatch.setattr(rdunet, "_CHAIN_DENSE", 0)
     torch.manual_seed(5)
     net = b2.RDUNet(base_filters=32).to(DEV).eval()
     net.precision = "fp16"
@@ -337,3 +338,36 @@ def test_fused_and_per_layer_networks_agree(built_lib, monkeypatch):
         layered = net(x)
         assert len(net.plan(2, 64, 80).launches) == 68
     assert float((fused - layered).abs().max()) < 5e-3
+
+
+@pytest.mark.parametrize("F,B,H,W,prec", [
+    (32, 1, 256, 256, "fp16"),      # batch 1: under-filled grids, N split to 64 at the deep levels (forced chains)
+    (32, 3, 128, 136, "fp16"),      # ragged tiles, odd batch (odd CTA of the last pair idles)
+    (32, 8, 256, 256, "bf16"),      # full grids, MT = 2 at levels 1-2
+    (64, 2, 64, 72, "bf16"),        # every level chained (no fused 32-channel block)
+    (16, 2, 128, 128, "fp16"),      # narrow levels fall back to the per-layer launches where the pair kernel does not apply
+])
+def test_chained_and_per_layer_dense_blocks_are_bit_equal(built_lib, monkeypatch, F, B, H, W, prec):
+    """conv_0..conv_3 of a DenoisingBlock as ONE persistent launch with per-tile dependencies
+    (csrc/conv3x3_chain_sm100.cu) vs the four launches it replaces: same tiles, same MMA order -> identical bits,
+    on the first call and on CUDA-graph replays (the dependency counters are monotonic across launches)."""
+    import vub_image_denoising_b200 as b2
+    from vub_image_denoising_b200 import rdunet
+    torch.manual_seed(11)
+    net = b2.RDUNet(base_filters=F).to(DEV).eval()
+    net.precision = prec
+    x = torch.rand(B, 3, H, W, device=DEV) * 2 - 1
+    with torch.no_grad():
+        monkeypatch.setattr(rdunet, "_CHAIN_DENSE", 2)       # also where the dispatch would launch layer by layer
+        net.invalidate_plans()
+        chained = [net(x).clone() for _ in range(4)]          # eager, graph capture, two replays
+        plan = net.plan(B, H, W)
+        n_chain = sum(isinstance(a, rdunet._Chain) for a in plan.launches)
+        monkeypatch.setattr(rdunet, "_CHAIN_DENSE", 0)
+        net.invalidate_plans()
+        layered = net(x)
+        assert not any(isinstance(a, rdunet._Chain) for a in net.plan(B, H, W).launches)
+    if F >= 32:
+        assert n_chain >= 6, n_chain
+    for y in chained:
+        assert torch.equal(y, layered)

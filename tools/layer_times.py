@@ -33,7 +33,7 @@ for i, info in enumerate(plan.layer_info):
     ms = sum(evs[r][i].elapsed_time(evs[r][i + 1]) for r in range(reps)) / reps
     tot += ms
     tf = info["flops"] / ms / 1e9
-    kind = {0: "conv3x3", 1: "down", 2: "up", 4: "denseblk"}[info["mode"]]
+    kind = {0: "conv3x3", 1: "down", 2: "up", 4: "denseblk", 5: "chain4"}[info["mode"]]
     key = f"{kind} N={min(info['cout'], 256) if kind != 'up' else 256}"
     g = groups.setdefault(key, [0.0, 0.0])
     g[0] += ms

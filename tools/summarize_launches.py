@@ -14,7 +14,7 @@ import re
 import sys
 from collections import OrderedDict
 
-TENSOR = ("conv3x3_slab_kernel", "conv3x3_slab2_kernel", "igemm_kernel", "dense_block_kernel")
+TENSOR = ("conv3x3_slab_kernel", "conv3x3_slab2_kernel", "conv3x3_chain_kernel", "igemm_kernel", "dense_block_kernel")
 
 
 def short(name: str) -> str:

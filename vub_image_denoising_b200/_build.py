@@ -54,17 +54,27 @@ def is_fresh() -> bool:
     return LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == _digest()
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every csrc/*.cu for sm_100a and link libb200dn.so. Returns the library path."""
+def build_lib(force: bool = False, verbose: bool = False, variant: str = "", defines: tuple = ()) -> Path:
+    """Compile every csrc/*.cu for sm_100a and link libb200dn.so. Returns the library path.
+
+    variant / defines: a diagnostics build next to the product library (`libb200dn_<variant>.so`, objects under
+    build/<variant>/), e.g. variant="timeline", defines=("B200DN_TIMELINE",) for tools/launch_timeline.py; it is
+    loaded only when B200DN_LIB points at it."""
+    if variant:
+        return _build(PKG_DIR / f"libb200dn_{variant}.so", BUILD_DIR / variant, [f"-D{d}" for d in defines], None, verbose)
     if not force and is_fresh():
         return LIB_PATH
+    return _build(LIB_PATH, BUILD_DIR, [], STAMP, verbose)
+
+
+def _build(lib_path: Path, build_dir: Path, extra: list, stamp, verbose: bool) -> Path:
     nvcc = _nvcc()
-    BUILD_DIR.mkdir(exist_ok=True)
+    build_dir.mkdir(parents=True, exist_ok=True)
     logs: dict[str, str] = {}
 
     def compile_one(src: Path) -> Path:
-        obj = BUILD_DIR / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        obj = build_dir / (src.stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         logs[src.name] = r.stdout + r.stderr
         if r.returncode != 0:
@@ -73,16 +83,20 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *map(str, objs)]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib_path), *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    (BUILD_DIR / "ptxas.log").write_text("\n".join(f"== {k}\n{v}" for k, v in sorted(logs.items())))
-    STAMP.write_text(_digest())
+    (build_dir / "ptxas.log").write_text("\n".join(f"== {k}\n{v}" for k, v in sorted(logs.items())))
+    if stamp is not None:
+        stamp.write_text(_digest())
     if verbose:
-        print((BUILD_DIR / "ptxas.log").read_text(), file=sys.stderr)
-    return LIB_PATH
+        print((build_dir / "ptxas.log").read_text(), file=sys.stderr)
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--timeline" in sys.argv:
+        print(build_lib(variant="timeline", defines=("B200DN_TIMELINE",), verbose="-v" in sys.argv))
+    else:
+        print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

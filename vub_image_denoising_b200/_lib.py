@@ -6,10 +6,12 @@ module raises; nothing here (or anywhere in the package) falls back to PyTorch/C
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "libb200dn.so"
+# B200DN_LIB: load a diagnostics build of the same sources instead (python -m vub_image_denoising_b200._build --timeline)
+LIB_PATH = Path(os.environ["B200DN_LIB"]) if os.environ.get("B200DN_LIB") else PKG_DIR / "libb200dn.so"
 
 ABI_VERSION = 2
 
@@ -29,6 +31,7 @@ EXPORTS = (
     "b200dn_igemm", "b200dn_igemm_plan", "b200dn_igemm_prepare", "b200dn_igemm_rebind_nchw", "b200dn_igemm_launch",
     "b200dn_igemm_launch_list", "b200dn_igemm_release", "b200dn_conv_in",
     "b200dn_dense_block_weight_bytes", "b200dn_pack_dense_block_weights", "b200dn_dense_block_prepare",
+    "b200dn_conv_chain_workspace_bytes", "b200dn_conv_chain_prepare",
     "b200dn_sampler_step", "b200dn_lerp",
     "b200dn_psnr_sse", "b200dn_ssim", "b200dn_psnr_sse_workspace_bytes", "b200dn_ssim_workspace_bytes",
     "b200dn_welch_psd", "b200dn_welch_psd_workspace_bytes",
@@ -71,6 +74,8 @@ class IgemmPlanInfo(C.Structure):
         "stage_bytes", "w_taps", "tmem_cols", "epi_staged", "data_bytes_used", "data_bytes_budget")]
 
 
+E_ARG, E_CUDA, E_UNSUP = -1, -2, -3      # B200DN_E_*
+
 _lib = None
 
 
@@ -82,8 +87,7 @@ def _check_fresh() -> None:
     """The .so is git-ignored and travels with the snapshot: refuse to run against a binary whose recorded source
     digest (build/sources.sha256, written by _build.build_lib) no longer matches csrc/ + include/b200dn.h, so that GPU
     parity results always reflect the sources at HEAD.  B200DN_ALLOW_STALE=1 skips the check."""
-    import os
-    if os.environ.get("B200DN_ALLOW_STALE") == "1":
+    if os.environ.get("B200DN_ALLOW_STALE") == "1" or os.environ.get("B200DN_LIB"):
         return
     from . import _build
     if _build.STAMP.exists() and _build.STAMP.read_text().strip() != _build._digest():
@@ -124,6 +128,9 @@ def lib() -> C.CDLL:
     L.b200dn_dense_block_weight_bytes.argtypes = [i32]
     L.b200dn_pack_dense_block_weights.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     L.b200dn_dense_block_prepare.argtypes = [C.POINTER(DenseBlockArgs), C.POINTER(vp)]
+    L.b200dn_conv_chain_workspace_bytes.restype = i64
+    L.b200dn_conv_chain_workspace_bytes.argtypes = [C.POINTER(IgemmArgs), i32]
+    L.b200dn_conv_chain_prepare.argtypes = [C.POINTER(IgemmArgs), i32, vp, i32, C.POINTER(vp)]
     L.b200dn_conv_in.argtypes = [vp, i32, i32, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp]
     L.b200dn_sampler_step.argtypes = [vp, vp, vp, vp, f32, f32, f32, f32, vp, i64, vp]
     L.b200dn_lerp.argtypes = [vp, vp, f32, f32, vp, i64, vp]
@@ -144,7 +151,8 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)
         if name not in ("b200dn_last_error", "b200dn_packed_weight_bytes", "b200dn_igemm_release",
                         "b200dn_psnr_sse_workspace_bytes", "b200dn_ssim_workspace_bytes",
-                        "b200dn_welch_psd_workspace_bytes", "b200dn_dense_block_weight_bytes"):
+                        "b200dn_welch_psd_workspace_bytes", "b200dn_dense_block_weight_bytes",
+                        "b200dn_conv_chain_workspace_bytes"):
             fn.restype = i32
     if L.b200dn_abi_version() != ABI_VERSION:
         raise RuntimeError("libb200dn.so ABI version mismatch; rebuild the library")

@@ -38,8 +38,10 @@ int device_sm_count();
 int require_sm100();   // 0 if the current device is compute capability 10.x
 // launch a persistent tensor-core kernel, with programmatic stream serialization unless B200DN_PDL=0
 // (cluster > 1: thread-block cluster of that many CTAs along x)
+// cooperative: the grid is launched only when all of its CTAs can be resident at once (kernels whose CTAs wait on
+// each other)
 cudaError_t launch_pdl(const void* kernel, int grid, int threads, size_t smem, cudaStream_t stream, void* params,
-                       int cluster = 1);
+                       int cluster = 1, bool cooperative = false);
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) function attribute: a process that drives
 // several GPUs must opt every kernel in on each of them.  `done` is a per-family table indexed by device ordinal.
 constexpr int kMaxDevices = 64;

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
   const int rank = static_cast<int>(cluster_ctarank());
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  if (threadIdx.x == 0) TL_MARK(p, TL_ENTRY);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA0);
@@ -132,10 +133,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
   cluster_sync_all();   // barrier inits and the TMEM allocation of BOTH CTAs are visible before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (threadIdx.x == 0) TL_MARK(p, TL_SETUP);
   griddep_launch_dependents();
   // the W producer only reads the packed weights (static data): it fills its ring while the previous kernel of the
   // stream is still running; every other role touches activations and waits for it
   if (warp != 2) griddep_wait();
+  if (threadIdx.x == 0) TL_MARK(p, TL_DEP);
+  [[maybe_unused]] bool tl_first = false;
 
   const int num_pair_tiles = p.num_tiles;   // pair tiles
   const int block_n = p.block_n, half_n = p.block_n >> 1;
@@ -238,6 +242,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
         for (int kc = 0; kc < kc_iters; ++kc) {
           const int nk = (cb != n_cblk - 1) ? BLOCK_K / 16 : last_k16;
           mbar_wait(bars + B_SLAB_FULL + s * 8, sph);
+          if (j == 0 && lane == 0) TL_MARK_ONCE(p, TL_MMA0, tl_first);
           const uint32_t slab = smem_base + static_cast<uint32_t>(s * slab_bytes) + static_cast<uint32_t>(j * TH) * pitch;
           uint64_t arow = make_sw128_desc(slab, pitch);
           issue_slab_block_streamed_n<true>(nk, w_taps, d, arow, row_step, wr, tap_step, idesc, accumulate);
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
           if (++cb == n_cblk) cb = 0;
         }
       }
+      if (j == 0 && lane == 0) TL_MARK(p, TL_MMA_END);
     }
   } else if (warp >= 4) {
     // ======================================================= epilogue (both CTAs, own accumulators)
@@ -285,6 +291,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
 
       mbar_wait(bars + B_TFULL + acc * 8, acc_phase);
       tc_fence_after();
+      if (we == 0 && lane == 0) TL_MARK_ONCE(p, TL_ACC0, tl_first);
 
 #pragma unroll 1
       for (int j = 0; j < MT; ++j) {
@@ -304,6 +311,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
       }
     }
     sat_report(ea.sat_flag, satm);
+    if (we == 0 && lane == 0) TL_MARK(p, TL_EPI_END);
   }
 
   // Neither CTA may leave (or free its TMEM) while the other can still read its shared memory through an MMA or
@@ -314,6 +322,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv3x3_slab2_kernel(const __g
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
+#ifdef B200DN_TIMELINE
+  if (threadIdx.x == 0 && p.tl != nullptr && blockIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.tl[TL_SM] = smid;
+    TL_MARK(p, TL_EXIT);
+  }
+#endif
 }
 
 SmemOptIn g_smem_opt_in;

@@ -54,6 +54,7 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
+  if (threadIdx.x == 0) TL_MARK(p, TL_ENTRY);
   uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
   const uint32_t bars = smem_base + DATA_BYTES;
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + DATA_BYTES + B_TMEM_PTR);
@@ -94,11 +95,13 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (threadIdx.x == 0) TL_MARK(p, TL_SETUP);
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel of
   // the stream; let the next kernel start its own prologue on idle SMs, then wait for our producer to finish before
   // any activation memory is touched (packed weights / bias are static and need no wait).
   griddep_launch_dependents();
   if (warp != 2) griddep_wait();   // the W producer (resident or streamed) only reads static data
+  if (threadIdx.x == 0) TL_MARK(p, TL_DEP);
 
   const int num_tiles = p.num_tiles, grid = gridDim.x;
   const int num_n_tiles = p.num_n_tiles, n_tiles_per_group = p.n_tiles_per_group, block_n = p.block_n;
@@ -356,6 +359,7 @@ conv3x3_slab_kernel(const __grid_constant__ KParams p) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
+  if (threadIdx.x == 0) TL_MARK(p, TL_EXIT);
 }
 
 SmemOptIn g_smem_opt_in;

@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
   float* s_slope = s_bias + NACC;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TL_MARK(p, TL_ENTRY);
 
   if (warp == W_PRODUCER && lane == 0) {
     tma_prefetch_desc(&p.tmX);
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (threadIdx.x == 0) TL_MARK(p, TL_SETUP);
   griddep_launch_dependents();
 
   const int num_regions = p.num_regions, grid = gridDim.x;
@@ -423,6 +425,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
+  if (threadIdx.x == 0) TL_MARK(p, TL_EXIT);
 }
 
 // [pass][tap][n][k] 16-bit from the four OIHW fp32 conv weights of a block
@@ -477,6 +480,13 @@ int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_
   f.in = a.in, f.in_ctot = a.in_ctot, f.out = a.out, f.out_ctot = a.out_ctot, f.out_coff = a.out_coff;
   f.sat_flag = a.sat_flag;
   f.dbg = reinterpret_cast<long long*>(a.timeline);
+#ifdef B200DN_TIMELINE
+  {
+    char label[96];
+    snprintf(label, sizeof(label), "dense_block %dx%dx%d c32", a.B, a.H, a.W);
+    f.tl = timeline_slots(label);
+  }
+#endif
   const CUtensorMapDataType dt = f.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   uint32_t estr[5] = {1, 1, 1, 1, 1};
   {

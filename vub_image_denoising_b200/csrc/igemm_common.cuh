@@ -51,7 +51,37 @@ struct __align__(64) KParams {
   const float* res_nchw;
   int res_bmod;
   int* sat_flag;         // optional: OR'ed with 1 when an fp16-stored output saturated (|v| >= 65504) or was NaN
+#ifdef B200DN_TIMELINE
+  unsigned long long* tl;   // diagnostics build only: 16 %globaltimer slots of this launch (CTA 0), see TL_MARK
+#endif
 };
+
+// Launch timeline (diagnostics build, -DB200DN_TIMELINE; tools/launch_timeline.py): CTA 0 of every tensor-core launch
+// stores %globaltimer at fixed points, so the hand-off between dependent launches of a small-batch forward (exit of
+// launch n -> entry / griddepcontrol.wait return / first MMA / first drained accumulator of launch n + 1) can be read
+// on one clock.  Compiled out of the product library.
+enum { TL_ENTRY = 0, TL_SETUP = 1, TL_DEP = 2, TL_MMA0 = 3, TL_MMA_END = 4, TL_ACC0 = 5, TL_EPI_END = 6, TL_EXIT = 7, TL_SM = 8 };
+#ifdef B200DN_TIMELINE
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL_MARK(p, slot)                                          \
+  do {                                                            \
+    if ((p).tl != nullptr && blockIdx.x == 0) (p).tl[slot] = tl_now(); \
+  } while (0)
+#define TL_MARK_ONCE(p, slot, flag)                               \
+  do {                                                            \
+    if (!(flag)) {                                                \
+      (flag) = true;                                              \
+      TL_MARK(p, slot);                                           \
+    }                                                             \
+  } while (0)
+#else
+#define TL_MARK(p, slot) do {} while (0)
+#define TL_MARK_ONCE(p, slot, flag) do {} while (0)
+#endif
 
 struct TileCoord {
   int b, y0, x0, grp, n0;
@@ -552,6 +582,23 @@ struct __align__(64) FusedParams {
   int out_ctot, out_coff;
   int* sat_flag;
   long long* dbg;                // optional timeline buffer (tools/dense_block_timeline.py): CTA 0 logs (event, clock64)
+#ifdef B200DN_TIMELINE
+  unsigned long long* tl;        // diagnostics build only: the launch-timeline slots (TL_MARK)
+#endif
+};
+
+// parameter block of the multi-layer chain kernel (conv3x3_chain_sm100.cu): the layers' own parameter blocks (ring
+// geometry unified by the host) + the work list and the inter-tile dependency counters
+constexpr int CHAIN_MAX_LAYERS = 4;
+struct __align__(64) ChainParams {
+  KParams L[CHAIN_MAX_LAYERS];
+  int n_layers;
+  int item_base[CHAIN_MAX_LAYERS + 1];   // first work item (pair tile) of each layer, layer-major
+  int flag_need[CHAIN_MAX_LAYERS];       // arrivals per launch that complete a spatial tile of layer l
+  int nmax;                              // TMEM columns between accumulators (largest N of the chain)
+  int tmem_cols;
+  uint32_t* flags;                       // [n_layers - 1][num_m_tiles] monotonic arrival counters
+  uint32_t* sync;                        // [0] launches completed, [1] CTAs that left the current launch
 };
 
 // A fully resolved launch: kernel variant, launch geometry and the parameter block (with its encoded tensor maps).
@@ -559,15 +606,24 @@ struct __align__(64) FusedParams {
 struct LaunchCfg {
   KParams p;          // kind 0: the per-layer implicit-GEMM kernels
   FusedParams f;      // kind 1: the fused dense block
+  ChainParams c;      // kind 2: several dependent 3x3 layers in one launch
   int kind;
   const void* kernel;
   int grid, threads, smem, cluster;
+  int cooperative;    // all CTAs must be co-resident (kind 2)
 };
+#ifdef B200DN_TIMELINE
+// 16 device slots for the next configured launch, labelled for the dump (igemm_sm100.cu)
+unsigned long long* timeline_slots(const char* label);
+#endif
 using PFN_encodeTiled = PFN_cuTensorMapEncodeTiled;
 // the driver's cuTensorMapEncodeTiled entry point (igemm_sm100.cu); 0 on success
 int get_tensor_map_encoder(PFN_encodeTiled* fn);
 // fused dense block (dense_block_sm100.cu): validate, encode, resolve
 int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_encodeTiled encode_fn);
+// chain of dependent 3x3 layers (conv3x3_chain_sm100.cu): B200DN_E_UNSUP when the layers do not qualify
+size_t conv_chain_workspace_bytes(const b200dn_igemm_args* layers, int n);
+int configure_conv_chain(const b200dn_igemm_args* layers, int n, void* workspace, int flags, LaunchCfg* cfg);
 // slab-kernel resolver (conv3x3_slab_sm100.cu); cfg->p is fully populated by igemm_configure.  Picks the template
 // variant and opts it in to its dynamic shared memory on the current device.
 int resolve_conv3x3_slab(LaunchCfg* cfg, int grid);
@@ -583,4 +639,8 @@ constexpr int SLAB_TILE_W = 8;    // output tile: 8 wide x 16 tall pixels per ac
 constexpr int SLAB_TILE_H = 16;
 
 }  // namespace igemm
+
+// igemm_sm100.cu: validate `a`, choose kernel family / tiling / ring sizes, encode the tensor maps into `cfg`
+int igemm_configure(const b200dn_igemm_args& a, igemm::LaunchCfg* cfg, b200dn_igemm_plan_info* info = nullptr,
+                    int sms_override = 0);
 }  // namespace b200dn

@@ -21,6 +21,11 @@
 //   warps 4..7      : epilogue.  tcgen05.ld -> +bias -> PReLU -> (+residual) -> 16-bit planes into the
 //                     NHWC channel slice, or fp32 NCHW (+fp32 NCHW residual) for the output block.
 #include "igemm_common.cuh"
+#ifdef B200DN_TIMELINE
+#include <mutex>
+#include <string>
+#include <vector>
+#endif
 
 #include <mutex>
 #include <new>
@@ -68,6 +73,7 @@ igemm_kernel(const __grid_constant__ KParams p) {
   const uint32_t smem_base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - raw_u32);
   const uint32_t bars = smem_base + DATA_BYTES;
+  if (threadIdx.x == 0) TL_MARK(p, TL_ENTRY);
   // barrier map: full[8] @0, empty[8] @64, tmem_full[2] @128, tmem_empty[2] @144, tmem ptr @160
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem_gen + DATA_BYTES + 160);
   float* epi_bias = reinterpret_cast<float*>(smem_gen + DATA_BYTES + 256);  // [2][MAX_N]
@@ -103,11 +109,13 @@ igemm_kernel(const __grid_constant__ KParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (threadIdx.x == 0) TL_MARK(p, TL_SETUP);
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the previous kernel of
   // the stream; let the next kernel start its own prologue on idle SMs, then wait for our producer to finish before
   // any activation memory is touched (packed weights / bias are static and need no wait).
   griddep_launch_dependents();
   if (warp != 2) griddep_wait();   // the W producer only reads static data: it runs ahead of the previous kernel's tail
+  if (threadIdx.x == 0) TL_MARK(p, TL_DEP);
 
   // Loop-invariant parameters live in registers: every asm volatile("memory") below would otherwise force the
   // compiler to re-read them from the constant bank inside the issue loops.
@@ -311,6 +319,7 @@ igemm_kernel(const __grid_constant__ KParams p) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
+  if (threadIdx.x == 0) TL_MARK(p, TL_EXIT);
 }
 
 // ------------------------------------------------------------------ host side
@@ -425,8 +434,7 @@ CUtensorMapL2promotion a_l2_promotion() {
 
 // Validate `a`, choose the kernel family / tiling / ring sizes and — unless this is a plan-only query (`info` set) —
 // encode the tensor maps and resolve the kernel variant into `cfg`.
-int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_plan_info* info = nullptr,
-                    int sms_override = 0) {
+int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_plan_info* info, int sms_override) {
   B200DN_CHECK_ARG(a.mode >= 0 && a.mode <= 3, "igemm: bad mode %d", a.mode);
   B200DN_CHECK_ARG(a.prec >= 0 && a.prec <= 4, "igemm: bad prec %d", a.prec);
   B200DN_CHECK_ARG(a.B > 0 && a.H > 0 && a.W > 0 && a.cin > 0 && a.cout > 0, "igemm: non-positive dims");
@@ -688,6 +696,16 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
   }
 
   cfg->kind = 0;
+  cfg->cooperative = 0;
+#ifdef B200DN_TIMELINE
+  {
+    char label[96];
+    snprintf(label, sizeof(label), "%s %dx%dx%d cin %d cout %d N %d mt %d %s", a.mode == B200DN_MODE_CONV3X3 ? "conv3x3"
+             : a.mode == B200DN_MODE_DOWN2X2 ? "down" : "up", a.B, a.H, a.W, a.cin, a.cout, block_n, mt,
+             slab ? (p.cta2 ? "pairs" : p.wres ? "wres" : "slab") : "tap");
+    p.tl = igemm::timeline_slots(label);
+  }
+#endif
   if (slab && p.cta2) return resolve_conv3x3_slab2(cfg, 2 * clusters);
   if (slab) return resolve_conv3x3_slab(cfg, grid);
 
@@ -708,13 +726,33 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
 
 int igemm_launch_cfg(const LaunchCfg& cfg, cudaStream_t stream) {
   // the parameter block is copied by the launch itself; nothing is re-encoded here
-  void* params = cfg.kind == 1 ? static_cast<void*>(const_cast<FusedParams*>(&cfg.f))
-                               : static_cast<void*>(const_cast<KParams*>(&cfg.p));
-  B200DN_CUDA(launch_pdl(cfg.kernel, cfg.grid, cfg.threads, static_cast<size_t>(cfg.smem), stream, params, cfg.cluster));
+  void* params = cfg.kind == 1   ? static_cast<void*>(const_cast<FusedParams*>(&cfg.f))
+                 : cfg.kind == 2 ? static_cast<void*>(const_cast<ChainParams*>(&cfg.c))
+                                 : static_cast<void*>(const_cast<KParams*>(&cfg.p));
+  B200DN_CUDA(launch_pdl(cfg.kernel, cfg.grid, cfg.threads, static_cast<size_t>(cfg.smem), stream, params, cfg.cluster,
+                         cfg.cooperative != 0));
   return 0;
 }
 
 namespace igemm {
+#ifdef B200DN_TIMELINE
+namespace {
+constexpr int TL_MAX_LAUNCHES = 4096;
+unsigned long long* g_tl_base = nullptr;
+std::vector<std::string> g_tl_labels;
+std::mutex g_tl_mutex;
+}  // namespace
+unsigned long long* timeline_slots(const char* label) {
+  std::lock_guard<std::mutex> lock(g_tl_mutex);
+  if (g_tl_base == nullptr) {
+    if (cudaMalloc(&g_tl_base, TL_MAX_LAUNCHES * 16 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+    cudaMemset(g_tl_base, 0, TL_MAX_LAUNCHES * 16 * sizeof(unsigned long long));
+  }
+  if (static_cast<int>(g_tl_labels.size()) >= TL_MAX_LAUNCHES) return nullptr;
+  g_tl_labels.emplace_back(label);
+  return g_tl_base + (g_tl_labels.size() - 1) * 16;
+}
+#endif
 int get_tensor_map_encoder(PFN_encodeTiled* fn) {
   if (int rc = get_encoder()) return rc;
   *fn = g_encode;
@@ -723,6 +761,29 @@ int get_tensor_map_encoder(PFN_encodeTiled* fn) {
 }  // namespace igemm
 
 }  // namespace b200dn
+
+#ifdef B200DN_TIMELINE
+// diagnostics build only (not in include/b200dn.h): one line per configured launch, the 9 slots in ns relative to `t0`
+extern "C" int b200dn_debug_timeline_dump(const char* path) {
+  using namespace b200dn::igemm;
+  std::lock_guard<std::mutex> lock(g_tl_mutex);
+  if (g_tl_base == nullptr) return -1;
+  cudaDeviceSynchronize();
+  const size_t n = g_tl_labels.size();
+  std::vector<unsigned long long> h(n * 16);
+  if (cudaMemcpy(h.data(), g_tl_base, n * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  FILE* f = fopen(path, "w");
+  if (!f) return -3;
+  fprintf(f, "# launch entry setup dep mma0 mma_end acc0 epi_end exit sm | label   (ns, absolute %%globaltimer; 0 = not recorded)\n");
+  for (size_t i = 0; i < n; ++i) {
+    fprintf(f, "%zu", i);
+    for (int k = 0; k < 9; ++k) fprintf(f, " %llu", h[i * 16 + k]);
+    fprintf(f, " | %s\n", g_tl_labels[i].c_str());
+  }
+  fclose(f);
+  return static_cast<int>(n);
+}
+#endif
 
 // the opaque handle of include/b200dn.h
 struct b200dn_igemm_prepared {
@@ -785,6 +846,35 @@ extern "C" int b200dn_dense_block_prepare(const b200dn_dense_block_args* args, b
     return B200DN_E_ARG;
   }
   if (int rc = b200dn::igemm::configure_dense_block(*args, &h->cfg, enc)) {
+    delete h;
+    return rc;
+  }
+  h->out_kind = B200DN_OUT_NHWC16;
+  *out = h;
+  return 0;
+}
+
+extern "C" int64_t b200dn_conv_chain_workspace_bytes(const b200dn_igemm_args* layers, int n_layers) {
+  if (!layers || n_layers < 1) {
+    b200dn::set_error("conv_chain_workspace_bytes: bad arguments");
+    return B200DN_E_ARG;
+  }
+  return static_cast<int64_t>(b200dn::igemm::conv_chain_workspace_bytes(layers, n_layers));
+}
+
+extern "C" int b200dn_conv_chain_prepare(const b200dn_igemm_args* layers, int n_layers, void* workspace, int flags,
+                                         b200dn_igemm_prepared** out) {
+  if (!layers || !out) {
+    b200dn::set_error("conv_chain_prepare: null layers / out");
+    return B200DN_E_ARG;
+  }
+  *out = nullptr;
+  b200dn_igemm_prepared* h = new (std::nothrow) b200dn_igemm_prepared;
+  if (!h) {
+    b200dn::set_error("conv_chain_prepare: out of host memory");
+    return B200DN_E_ARG;
+  }
+  if (int rc = b200dn::igemm::configure_conv_chain(layers, n_layers, workspace, flags, &h->cfg)) {
     delete h;
     return rc;
   }

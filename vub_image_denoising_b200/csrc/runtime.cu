@@ -90,7 +90,7 @@ int ensure_max_dyn_smem(SmemOptIn& st, const void* const* kernels, int n, int by
 }
 
 cudaError_t launch_pdl(const void* kernel, int grid, int threads, size_t smem, cudaStream_t stream, void* params,
-                       int cluster) {
+                       int cluster, bool cooperative) {
   static const int pdl = [] {
     const char* e = getenv("B200DN_PDL");
     return e ? atoi(e) : 1;
@@ -101,8 +101,13 @@ cudaError_t launch_pdl(const void* kernel, int grid, int threads, size_t smem, c
   cfg.blockDim = dim3(static_cast<unsigned>(threads));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int n = 0;
+  if (cooperative) {
+    attr[n].id = cudaLaunchAttributeCooperative;
+    attr[n].val.cooperative = 1;
+    ++n;
+  }
   if (cluster > 1) {
     attr[n].id = cudaLaunchAttributeClusterDimension;
     attr[n].val.clusterDim.x = static_cast<unsigned>(cluster);

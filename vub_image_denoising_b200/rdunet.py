@@ -33,6 +33,20 @@ _USE_GRAPH = os.environ.get("B200DN_GRAPH", "1") != "0"   # replay nn.Module for
 # 32-channel DenoisingBlocks (level 0 of base_filters = 32) run as ONE fused kernel instead of four launches
 _FUSE_DENSE = os.environ.get("B200DN_FUSED_DENSE", "1") != "0"
 MODE_DENSE_BLOCK = 4     # layer_info "mode" of a fused block (the per-layer modes are _lib.MODE_*)
+# wider DenoisingBlocks (the single-plane modes): conv_0..conv_3 as ONE persistent launch whose tiles wait on the tiles
+# they read instead of on a launch boundary (csrc/conv3x3_chain_sm100.cu); bit-equal to the four launches it replaces
+# B200DN_CHAIN: 0 = never, 1 = where a layer has at least two rounds of tiles per SM pair (default), 2 = wherever it applies
+_CHAIN_DENSE = int(os.environ.get("B200DN_CHAIN", "1"))
+MODE_CONV_CHAIN = 5      # layer_info "mode" of such a chain
+
+
+class _Chain:
+    """The four b200dn_igemm_args of a DenoisingBlock, to be prepared as one chain launch (or one by one)."""
+
+    __slots__ = ("layers", "infos")
+
+    def __init__(self, layers, infos):
+        self.layers, self.infos = layers, infos
 
 
 # --------------------------------------------------------------------------- init
@@ -424,7 +438,7 @@ class ForwardPlan:
         return t.data_ptr()
 
     def _igemm(self, mode, conv, actv, src: _Act, cin, dst: Optional[_Act], coff, B, H, W, res: Optional[_Act] = None,
-               transposed=False, nchw=False) -> IgemmArgs:
+               transposed=False, nchw=False, collect: Optional[list] = None) -> IgemmArgs:
         a = IgemmArgs()
         a.mode, a.prec = mode, self.prec
         a.B, a.H, a.W = B, H, W
@@ -452,9 +466,13 @@ class ForwardPlan:
         taps = {_lib.MODE_CONV3X3: 9, _lib.MODE_DOWN2X2: 4, _lib.MODE_UP2X2: 4}[mode]
         pix = B * H * W if mode != _lib.MODE_DOWN2X2 else B * (H // 2) * (W // 2)
         self.flops += 2 * pix * taps * cin * cout
+        info = dict(mode=mode, H=H, W=W, cin=cin, cout=cout * (4 if transposed else 1),
+                    flops=2 * pix * taps * cin * cout, nchw=nchw)
+        if collect is not None:        # part of a chain: listed by the caller
+            collect.append((a, info))
+            return a
         self.launches.append(a)
-        self.layer_info.append(dict(mode=mode, H=H, W=W, cin=cin, cout=cout * (4 if transposed else 1),
-                                    flops=2 * pix * taps * cin * cout, nchw=nchw))
+        self.layer_info.append(info)
         return a
 
     def _fusable(self, C: int) -> bool:
@@ -496,11 +514,17 @@ class ForwardPlan:
             self._dense_fused(blk, src, dst, dst_coff, B, H, W, C)
             return
         g = C // 2
+        chain = [] if (_CHAIN_DENSE and self.prec in (_lib.PREC_BF16, _lib.PREC_FP16)) else None
         for k in range(3):
             self._igemm(_lib.MODE_CONV3X3, getattr(blk, f"conv_{k}"), getattr(blk, f"actv_{k}"),
-                        src, C + k * g, src, C + k * g, B, H, W)
+                        src, C + k * g, src, C + k * g, B, H, W, collect=chain)
         # conv_3 + PReLU, then `+ x` (RDUNet_model.py:114-115): residual = channels [0, C) of the block input
-        self._igemm(_lib.MODE_CONV3X3, blk.conv_3, blk.actv_3, src, C + 3 * g, dst, dst_coff, B, H, W, res=src)
+        self._igemm(_lib.MODE_CONV3X3, blk.conv_3, blk.actv_3, src, C + 3 * g, dst, dst_coff, B, H, W, res=src,
+                    collect=chain)
+        if chain is not None:
+            self.launches.append(_Chain([a for a, _ in chain], [i for _, i in chain]))
+            self.layer_info.append(dict(mode=MODE_CONV_CHAIN, H=H, W=W, cin=C, cout=C,
+                                        flops=sum(i["flops"] for _, i in chain), nchw=False))
 
     def _build(self, net: _RDUNetBase) -> None:
         B, H, W, F, dev, two = self.B, self.H, self.W, self.F, self.device, self.two
@@ -551,17 +575,39 @@ class ForwardPlan:
         self.out_args = self._igemm(_lib.MODE_CONV3X3, ob.conv_2, ob.actv_2, I0, F, None, 0, B, H, W, nchw=True)
         # prepare every launch once: validation, tiling plan and the 2-3 CUtensorMap encodes (~25 us of host time per
         # layer when done per call) happen here; run() then costs one C call that enqueues the 68 kernels
-        n = len(self.launches)
-        self._handles = (C.c_void_p * n)()
-        for i, a in enumerate(self.launches):
+        handles, launches, infos = [], [], []
+
+        def prepare_one(a, info):
+            h = C.c_void_p()
+            if a.out_kind == _lib.OUT_NCHW32:      # bound per call in run(); prepare wants a non-null placeholder
+                a.out_nchw = self._keep[0].data_ptr()
+            _lib.check(self.lib.b200dn_igemm_prepare(C.byref(a), C.byref(h)), f"igemm_prepare (launch {len(handles)})")
+            handles.append(h), launches.append(a), infos.append(info)
+
+        for a, info in zip(self.launches, self.layer_info):
             h = C.c_void_p()
             if isinstance(a, DenseBlockArgs):
-                _lib.check(self.lib.b200dn_dense_block_prepare(C.byref(a), C.byref(h)), f"dense_block_prepare (launch {i})")
+                _lib.check(self.lib.b200dn_dense_block_prepare(C.byref(a), C.byref(h)),
+                           f"dense_block_prepare (launch {len(handles)})")
+                handles.append(h), launches.append(a), infos.append(info)
+            elif isinstance(a, _Chain):
+                arr = (IgemmArgs * len(a.layers))(*a.layers)
+                nbytes = self.lib.b200dn_conv_chain_workspace_bytes(arr, len(a.layers))
+                ws = torch.zeros(max(int(nbytes), 64) // 4, dtype=torch.int32, device=self.device)
+                rc = self.lib.b200dn_conv_chain_prepare(arr, len(a.layers), ws.data_ptr(), 1 if _CHAIN_DENSE == 2 else 0,
+                                                        C.byref(h))
+                if rc == _lib.E_UNSUP:             # e.g. resident-weight or single-CTA layers: launch them one by one
+                    for la, li in zip(a.layers, a.infos):
+                        prepare_one(la, li)
+                else:
+                    _lib.check(rc, f"conv_chain_prepare (launch {len(handles)})")
+                    self._keep.extend((ws, arr))
+                    handles.append(h), launches.append(a), infos.append(info)
             else:
-                if a.out_kind == _lib.OUT_NCHW32:      # bound per call in run(); prepare wants a non-null placeholder
-                    a.out_nchw = self._keep[0].data_ptr()
-                _lib.check(self.lib.b200dn_igemm_prepare(C.byref(a), C.byref(h)), f"igemm_prepare (launch {i})")
-            self._handles[i] = h
+                prepare_one(a, info)
+        self.launches, self.layer_info = launches, infos
+        n = len(launches)
+        self._handles = (C.c_void_p * n)(*handles)
         self._out_handle = self._handles[n - 1]
         self._ready = torch.cuda.Event()
         self._ready.record(torch.cuda.current_stream(self.device))
