@@ -174,7 +174,8 @@ def test_down2x2(case, prec, built_lib):
     _check_slice(out_hi, out_lo, prec, 0, cout, ref, "down2x2")
 
 
-UP_CASES = [(1, 8, 16, 32), (2, 12, 20, 64), (1, 32, 32, 256), (1, 4, 4, 128)]
+# c <= 64: the four output phases are one N = 4c accumulator (folded); wider: one tile per phase
+UP_CASES = [(1, 8, 16, 32), (2, 12, 20, 64), (1, 32, 32, 256), (1, 4, 4, 128), (3, 24, 40, 48), (1, 16, 16, 16)]
 
 
 @pytest.mark.parametrize("prec", PRECS, ids=PREC_IDS)

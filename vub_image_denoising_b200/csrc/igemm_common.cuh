@@ -38,6 +38,7 @@ struct __align__(64) KParams {
   int w_taps;            // filter taps per streamed-W ring stage (1, or 3 = one filter row)
   int cta2, num_m_tiles; // CTA-pair kernel (cta_group::2): two spatial super tiles per W tile, one per CTA
   int epi_staged;        // smem-transposed epilogue with 128-byte-row global stores
+  int up_fold;           // transposed conv with 4 * cout <= 256: the four output phases are ONE N tile (A loaded once)
   const float* bias;
   const float* slope;
   int out_kind;

@@ -300,7 +300,24 @@ igemm_kernel(const __grid_constant__ KParams p) {
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>((acc * MT + j) * block_n + col0);
         const uint32_t rel = j == MT - 1 ? bars + 144 + acc * 8 : 0u;
-        if (staged) {
+        if (MODE == 2 && p.up_fold) {
+          // columns = [phase 0 | 1 | 2 | 3] x cout: this group drains phases 2 eg and 2 eg + 1 (EG == 2: MT == 1)
+#pragma unroll 1
+          for (int q = 0; q < 4 / EG; ++q) {
+            const int ph = eg * (4 / EG) + q, ky = ph >> 1, kx = ph & 1;
+            const uint32_t tq = taddr + static_cast<uint32_t>(q * cout);
+            const uint32_t relq = q == 4 / EG - 1 ? rel : 0u;
+            if (staged) {
+              RowMap rm;
+              rm.b = t.b, rm.y0 = t.y0, rm.x0 = t.x0 + j * TILE_W, rm.tw_shift = 4, rm.H = H, rm.W = W;
+              rm.up = 1, rm.ky = ky, rm.kx = kx;
+              epilogue_subtile_staged(ea, tq, cout, bs, ss, rm, we * 32, lane, 0, relq, stg, satm);
+            } else {
+              const int64_t op = (static_cast<int64_t>(t.b) * (2 * H) + (2 * y + ky)) * (2 * W) + (2 * x + kx);
+              epilogue_subtile(ea, tq, cout, bs, ss, valid, t.b, y, x, op, res_pix, 0, relq, satm);
+            }
+          }
+        } else if (staged) {
           RowMap rm;
           rm.b = t.b, rm.y0 = t.y0, rm.x0 = t.x0 + j * TILE_W, rm.tw_shift = 4, rm.H = H, rm.W = W;
           rm.up = up ? 1 : 0, rm.ky = t.grp >> 1, rm.kx = t.grp & 1;
@@ -394,6 +411,14 @@ int cta2_mode() {
   }();
   return mode;
 }
+// B200DN_UP_FOLD=0: transposed convs keep one tile per output phase even when all four fit one accumulator
+int up_fold_enabled() {
+  static int v = [] {
+    const char* e = getenv("B200DN_UP_FOLD");
+    return e ? atoi(e) : 1;
+  }();
+  return v;
+}
 // B200DN_SPLIT_N: smallest N tile the under-filled-grid heuristic may choose (default 64; 0 or 256 = never split)
 int split_n_floor() {
   static int v = [] {
@@ -481,6 +506,12 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
   int sms = info ? sms_override : device_sm_count();
   if (sms <= 0) return B200DN_E_CUDA;
   int block_n = a.block_n;
+  // Transposed conv whose four phases fit one accumulator (4 * cout <= 256, cout a multiple of 16: level 1 -> 0 of
+  // base_filters <= 32): N = [phase 0 | 1 | 2 | 3] in one tile.  The A tile is loaded once instead of four times and
+  // the per-tile pipeline round trips (4 UMMAs of K = 64 each) are paid once per pixel tile.
+  const bool up_fold = a.mode == B200DN_MODE_UP2X2 && block_n == 0 && a.m_tiles != 2 && up_fold_enabled() &&
+                       a.cout % 16 == 0 && 4 * a.cout <= MAX_N;
+  if (up_fold) block_n = 4 * a.cout;
   if (block_n == 0) {
     const int nt = cdiv(cout_pad, MAX_N);
     block_n = round_up(cdiv(cout_pad, nt), 16);
@@ -496,8 +527,9 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
   }
   B200DN_CHECK_ARG(block_n % 16 == 0 && block_n >= 16 && block_n <= MAX_N, "igemm: block_n %d invalid", block_n);
   p.block_n = block_n;
-  p.n_tiles_per_group = cdiv(cout_pad, block_n);
-  p.num_n_tiles = p.n_tiles_per_group * n_groups;
+  p.up_fold = up_fold ? 1 : 0;
+  p.n_tiles_per_group = up_fold ? 1 : cdiv(cout_pad, block_n);
+  p.num_n_tiles = up_fold ? 1 : p.n_tiles_per_group * n_groups;
   // accumulator tile: 16 x 8 pixels (tap kernel, sub-tiles side by side) or 8 x 16 (slab kernel, sub-tiles stacked)
   const int tw1 = slab ? SLAB_TILE_W : TILE_W, th1 = slab ? SLAB_TILE_H : TILE_H;
   // two A tiles per W tile (M = 256) when N is small enough for 4 accumulators in TMEM and there is enough
@@ -598,7 +630,7 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
   p.out_kind = a.out_kind;
   // staged (smem-transposed, 128-byte-row) epilogue: single-plane NHWC output in whole 64-channel groups
   // (the one-accumulator transposed-conv variant splits the columns over two epilogue groups: 64-channel groups per half)
-  const int epi_cols = (a.mode == B200DN_MODE_UP2X2 && mt == 1) ? block_n / 2 : block_n;
+  const int epi_cols = up_fold ? a.cout : (a.mode == B200DN_MODE_UP2X2 && mt == 1) ? block_n / 2 : block_n;
   p.epi_staged = (a.out_kind == B200DN_OUT_NHWC16 && !two_a && epi_cols % 64 == 0 && a.cout % 64 == 0 &&
                   a.out_coff % 64 == 0 && a.out_ctot % 8 == 0 && (staged_mode() == 1 || (staged_mode() == 2 && mt == 1))) ? 1 : 0;
   if (a.out_kind == B200DN_OUT_NHWC16) {
@@ -692,6 +724,7 @@ int igemm_configure(const b200dn_igemm_args& a, LaunchCfg* cfg, b200dn_igemm_pla
     // resident mode: all 9 taps per box; streamed: w_taps taps per box; CTA pairs: half of the N rows per CTA
     uint32_t box[3] = {BLOCK_K, static_cast<uint32_t>(p.cta2 ? block_n / 2 : block_n),
                        p.wres ? 9u : static_cast<uint32_t>(slab ? p.w_taps : 1)};
+    if (up_fold) box[1] = static_cast<uint32_t>(a.cout), box[2] = 4;   // [phase][cout] rows = the N = 4 * cout tile
     if (int rc = encode(&p.tmW, dt, 3, a.wpacked, dims, str, box, "W")) return rc;
   }
 
