@@ -196,6 +196,13 @@ int64_t b200dn_dense_block_weight_bytes(int channels);
 int b200dn_pack_dense_block_weights(const float* w0, const float* w1, const float* w2, const float* w3,
                                     int channels, int prec, void* packed, void* stream);
 int b200dn_dense_block_prepare(const b200dn_dense_block_args* args, b200dn_igemm_prepared** out);
+/* Optional: hand the block's bias / PReLU slopes to a prepared dense block as HOST values (bias_host[j], slope_host[j]:
+ * 16, 16, 16, 32 floats of conv_0..conv_3, the same numbers the device arrays of the args hold).  They then travel in
+ * the launch parameters (constant bank) and the epilogue reads them as instruction operands instead of staging them in
+ * shared memory — the kernel runs at the shared-memory bandwidth wall and the broadcast reads were 11 % of its
+ * shared-memory wavefronts.  Results are bit-identical.  May be called again to refresh the values. */
+int b200dn_dense_block_set_epilogue_constants(b200dn_igemm_prepared* prep, const float* const* bias_host,
+                                              const float* const* slope_host);
 
 /* ---- 2..4 DEPENDENT 3x3 convolutions of one resolution in one persistent launch (csrc/conv3x3_chain_sm100.cu) ------
  * layers[k] is a b200dn_igemm_args as b200dn_igemm takes it (MODE_CONV3X3, OUT_NHWC16, PREC_BF16 or PREC_FP16, all

@@ -305,6 +305,17 @@ def test_fused_dense_block(shape, prec, built_lib):
     _lib.check(L.b200dn_igemm_launch(h, st), "launch")
     _lib.check(L.b200dn_igemm_launch(h, st), "launch")          # relaunching a prepared block is idempotent
     torch.cuda.synchronize()
+    staged = out.clone()
+    # the same block with bias / slopes as host values in the launch parameters (constant bank): identical bits
+    out.fill_(7.0)
+    fp = C.POINTER(C.c_float)
+    hb, hs = [t.cpu() for t in bs], [t.cpu() for t in ss]
+    _lib.check(L.b200dn_dense_block_set_epilogue_constants(h, (fp * 4)(*[C.cast(t.data_ptr(), fp) for t in hb]),
+                                                           (fp * 4)(*[C.cast(t.data_ptr(), fp) for t in hs])), "set constants")
+    _lib.check(L.b200dn_igemm_launch(h, st), "launch")
+    torch.cuda.synchronize()
+    assert torch.equal(out, staged)
+    assert L.b200dn_dense_block_set_epilogue_constants(h, None, None) == -1
     L.b200dn_igemm_release(h)
     ref = _dense_block_ref(x[..., :32].permute(0, 3, 1, 2), ws, bs, ss, dt).cpu()
     got = out[..., 40:72].permute(0, 3, 1, 2).double().cpu()

@@ -31,6 +31,7 @@ EXPORTS = (
     "b200dn_igemm", "b200dn_igemm_plan", "b200dn_igemm_prepare", "b200dn_igemm_rebind_nchw", "b200dn_igemm_launch",
     "b200dn_igemm_launch_list", "b200dn_igemm_release", "b200dn_conv_in",
     "b200dn_dense_block_weight_bytes", "b200dn_pack_dense_block_weights", "b200dn_dense_block_prepare",
+    "b200dn_dense_block_set_epilogue_constants",
     "b200dn_conv_chain_workspace_bytes", "b200dn_conv_chain_prepare",
     "b200dn_sampler_step", "b200dn_lerp",
     "b200dn_psnr_sse", "b200dn_ssim", "b200dn_psnr_sse_workspace_bytes", "b200dn_ssim_workspace_bytes",
@@ -128,6 +129,7 @@ def lib() -> C.CDLL:
     L.b200dn_dense_block_weight_bytes.argtypes = [i32]
     L.b200dn_pack_dense_block_weights.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
     L.b200dn_dense_block_prepare.argtypes = [C.POINTER(DenseBlockArgs), C.POINTER(vp)]
+    L.b200dn_dense_block_set_epilogue_constants.argtypes = [vp, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.POINTER(C.c_float))]
     L.b200dn_conv_chain_workspace_bytes.restype = i64
     L.b200dn_conv_chain_workspace_bytes.argtypes = [C.POINTER(IgemmArgs), i32]
     L.b200dn_conv_chain_prepare.argtypes = [C.POINTER(IgemmArgs), i32, vp, i32, C.POINTER(vp)]

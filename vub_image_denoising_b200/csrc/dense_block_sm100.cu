@@ -173,6 +173,35 @@ __device__ __forceinline__ void bias_prelu_pack16(const uint32_t (&rr)[16], cons
     h[2 * q + 1] = pack2<kBf16>(a2, a3);
   }
 }
+// Both tiles of an epilogue group at once: bias / slopes are read from shared memory ONCE for the two rows (ncu: the
+// broadcast LDS.128 of the one-tile helper were 11 % of the kernel's shared-memory wavefronts, on a kernel that sits at
+// the shared-memory bandwidth wall).
+template <bool kBf16>
+__device__ __forceinline__ void bias_prelu_pack16_x2(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const float* bs,
+                                                     const float* ss, uint32_t (&ha)[8], uint32_t (&hb)[8]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bs);
+  const float4* s4 = reinterpret_cast<const float4*>(ss);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 bb = b4[q], sl = s4[q];
+    float a0 = __uint_as_float(ra[4 * q]) + bb.x, a1 = __uint_as_float(ra[4 * q + 1]) + bb.y;
+    float a2 = __uint_as_float(ra[4 * q + 2]) + bb.z, a3 = __uint_as_float(ra[4 * q + 3]) + bb.w;
+    float c0 = __uint_as_float(rb[4 * q]) + bb.x, c1 = __uint_as_float(rb[4 * q + 1]) + bb.y;
+    float c2 = __uint_as_float(rb[4 * q + 2]) + bb.z, c3 = __uint_as_float(rb[4 * q + 3]) + bb.w;
+    a0 = a0 > 0.f ? a0 : a0 * sl.x;
+    a1 = a1 > 0.f ? a1 : a1 * sl.y;
+    a2 = a2 > 0.f ? a2 : a2 * sl.z;
+    a3 = a3 > 0.f ? a3 : a3 * sl.w;
+    c0 = c0 > 0.f ? c0 : c0 * sl.x;
+    c1 = c1 > 0.f ? c1 : c1 * sl.y;
+    c2 = c2 > 0.f ? c2 : c2 * sl.z;
+    c3 = c3 > 0.f ? c3 : c3 * sl.w;
+    ha[2 * q] = pack2<kBf16>(a0, a1);
+    ha[2 * q + 1] = pack2<kBf16>(a2, a3);
+    hb[2 * q] = pack2<kBf16>(c0, c1);
+    hb[2 * q + 1] = pack2<kBf16>(c2, c3);
+  }
+}
 // the same with the 16-bit residual x (8 packed pairs) added after the activation (`out_3 + x`, RDUNet_model.py:115)
 template <bool kBf16>
 __device__ __forceinline__ void bias_prelu_res_pack16(const uint32_t (&rr)[16], const float* bs, const float* ss,
@@ -194,7 +223,37 @@ __device__ __forceinline__ void bias_prelu_res_pack16(const uint32_t (&rr)[16], 
   }
 }
 
-template <bool kBf16, bool kDbg>
+template <bool kBf16>
+__device__ __forceinline__ void bias_prelu_res_pack16_x2(const uint32_t (&ra)[16], const uint32_t (&rb)[16], const float* bs,
+                                                         const float* ss, const uint4& xa0, const uint4& xa1, const uint4& xb0,
+                                                         const uint4& xb1, uint32_t (&ha)[8], uint32_t (&hb)[8]) {
+  const float4* b4 = reinterpret_cast<const float4*>(bs);
+  const float4* s4 = reinterpret_cast<const float4*>(ss);
+  const uint32_t xa[8] = {xa0.x, xa0.y, xa0.z, xa0.w, xa1.x, xa1.y, xa1.z, xa1.w};
+  const uint32_t xb[8] = {xb0.x, xb0.y, xb0.z, xb0.w, xb1.x, xb1.y, xb1.z, xb1.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 bb = b4[q], sl = s4[q];
+    float a0 = __uint_as_float(ra[4 * q]) + bb.x, a1 = __uint_as_float(ra[4 * q + 1]) + bb.y;
+    float a2 = __uint_as_float(ra[4 * q + 2]) + bb.z, a3 = __uint_as_float(ra[4 * q + 3]) + bb.w;
+    float c0 = __uint_as_float(rb[4 * q]) + bb.x, c1 = __uint_as_float(rb[4 * q + 1]) + bb.y;
+    float c2 = __uint_as_float(rb[4 * q + 2]) + bb.z, c3 = __uint_as_float(rb[4 * q + 3]) + bb.w;
+    a0 = (a0 > 0.f ? a0 : a0 * sl.x) + cvt_lo<kBf16>(xa[2 * q]);
+    a1 = (a1 > 0.f ? a1 : a1 * sl.y) + cvt_hi<kBf16>(xa[2 * q]);
+    a2 = (a2 > 0.f ? a2 : a2 * sl.z) + cvt_lo<kBf16>(xa[2 * q + 1]);
+    a3 = (a3 > 0.f ? a3 : a3 * sl.w) + cvt_hi<kBf16>(xa[2 * q + 1]);
+    c0 = (c0 > 0.f ? c0 : c0 * sl.x) + cvt_lo<kBf16>(xb[2 * q]);
+    c1 = (c1 > 0.f ? c1 : c1 * sl.y) + cvt_hi<kBf16>(xb[2 * q]);
+    c2 = (c2 > 0.f ? c2 : c2 * sl.z) + cvt_lo<kBf16>(xb[2 * q + 1]);
+    c3 = (c3 > 0.f ? c3 : c3 * sl.w) + cvt_hi<kBf16>(xb[2 * q + 1]);
+    ha[2 * q] = pack2<kBf16>(a0, a1);
+    ha[2 * q + 1] = pack2<kBf16>(a2, a3);
+    hb[2 * q] = pack2<kBf16>(c0, c1);
+    hb[2 * q + 1] = pack2<kBf16>(c2, c3);
+  }
+}
+
+template <bool kBf16, bool kDbg, bool kConst>
 __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -204,6 +263,9 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sg + OFF_CTRL + DB_TMEM);
   float* s_bias = reinterpret_cast<float*>(sg + OFF_BIAS);
   float* s_slope = s_bias + NACC;
+  // epilogue operands: launch parameters (constant bank; indices become compile-time after unrolling) or shared memory
+  const float* e_bias = kConst ? p.cbias : s_bias;
+  const float* e_slope = kConst ? p.cslope : s_slope;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) TL_MARK(p, TL_ENTRY);
@@ -228,7 +290,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     tmem_relinquish();
   }
   // bias / slopes of the four convs in accumulator-column order (static data: no dependency on the previous kernel)
-  if (threadIdx.x < NACC) {
+  if (!kConst && threadIdx.x < NACC) {
     const int c = threadIdx.x;
     const int j = c < 48 ? c >> 4 : 3, k = c < 48 ? c & 15 : c - 48;
     s_bias[c] = __ldg(p.bias[j] + k);
@@ -315,8 +377,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
       const int gx = rx * RW - 4 + fx, gy_0 = ry * RH - 4 + fy0, gy_1 = gy_0 + 16;
       const bool col_in = gx >= 0 && gx < W;
       const bool img0 = col_in && gy_0 >= 0 && gy_0 < H, img1 = col_in && gy_1 >= 0 && gy_1 < H;
-#pragma unroll 1
-      for (int ps = 0; ps < 3; ++ps) {
+      auto pass_epilogue = [&](const int ps) {
         // ---- o_ps of both tiles: bias + PReLU -> 16-bit -> shared memory (32-byte swizzled rows), zeros outside the image
         const uint32_t par = static_cast<uint32_t>((it * 4 + ps) & 1);
         mbar_wait(bars + DB_TFULL + (2 * tx) * 8, par);
@@ -331,32 +392,40 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
         const bool ux = fx >= 1 + ps && fx < FP - 1 - ps;
         const bool use0 = ux && fy0 >= 1 + ps, use1 = ux && fy1 < FR - 1 - ps;      // fy0 <= 16, fy1 >= 17
         const uint32_t obase = ps == 0 ? OFF_O0 : ps == 1 ? OFF_O1 : OFF_O2;
-        uint32_t h[8];
-        if (use0) {
-          bias_prelu_pack16<kBf16>(ra, s_bias + ps * 16, s_slope + ps * 16, h);
-          if (watch && img0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
-          }
+        if (use0 || use1) {
+          uint32_t ha[8], hb[8];
+          bias_prelu_pack16_x2<kBf16>(ra, rb, e_bias + ps * 16, e_slope + ps * 16, ha, hb);
           const uint4 z = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(sg + obase + (po0 ^ sw0)) = img0 ? make_uint4(h[0], h[1], h[2], h[3]) : z;
-          *reinterpret_cast<uint4*>(sg + obase + ((po0 + 16u) ^ sw0)) = img0 ? make_uint4(h[4], h[5], h[6], h[7]) : z;
-        }
-        if (use1) {
-          bias_prelu_pack16<kBf16>(rb, s_bias + ps * 16, s_slope + ps * 16, h);
-          if (watch && img1) {
+          if (use0) {
+            if (watch && img0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
+              for (int j = 0; j < 8; ++j) satm = sat_track(satm, ha[j]);
+            }
+            *reinterpret_cast<uint4*>(sg + obase + (po0 ^ sw0)) = img0 ? make_uint4(ha[0], ha[1], ha[2], ha[3]) : z;
+            *reinterpret_cast<uint4*>(sg + obase + ((po0 + 16u) ^ sw0)) = img0 ? make_uint4(ha[4], ha[5], ha[6], ha[7]) : z;
           }
-          const uint4 z = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(sg + obase + (po1 ^ sw1)) = img1 ? make_uint4(h[0], h[1], h[2], h[3]) : z;
-          *reinterpret_cast<uint4*>(sg + obase + ((po1 + 16u) ^ sw1)) = img1 ? make_uint4(h[4], h[5], h[6], h[7]) : z;
+          if (use1) {
+            if (watch && img1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) satm = sat_track(satm, hb[j]);
+            }
+            *reinterpret_cast<uint4*>(sg + obase + (po1 ^ sw1)) = img1 ? make_uint4(hb[0], hb[1], hb[2], hb[3]) : z;
+            *reinterpret_cast<uint4*>(sg + obase + ((po1 + 16u) ^ sw1)) = img1 ? make_uint4(hb[4], hb[5], hb[6], hb[7]) : z;
+          }
         }
         fence_proxy_async_smem();     // generic-proxy stores -> visible to the UMMAs of the next pass
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + DB_OCOL + tx * 8);
         dl.log(DBG_EV(2 + tx, it, ps, 2 * tx, 2));     // o_ps written + arrived
+      };
+      if (kConst) {      // unrolled: the bias / slope indices are compile-time, i.e. c[0x0][...] operands of the FADD / FMUL
+        pass_epilogue(0);
+        pass_epilogue(1);
+        pass_epilogue(2);
+      } else {
+#pragma unroll 1
+        for (int ps = 0; ps < 3; ++ps) pass_epilogue(ps);
       }
       {
         // ---- pass 3: o3 + x -> global (NHWC 16-bit channel slice), region interior only; 16 columns of both tiles at a time
@@ -391,26 +460,28 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
             if (lane == 0) mbar_arrive(bars + DB_OCOL + tx * 8);      // TMEM columns of both tiles are free again
             dl.log(DBG_EV(2 + tx, it, 3, 2 * tx, 1));
           }
-          uint32_t h[8];
-          if (st0) {
-            bias_prelu_res_pack16<kBf16>(ra, s_bias + 48 + 16 * half, s_slope + 48 + 16 * half, x0[2 * half], x0[2 * half + 1], h);
-            if (watch) {
+          if (st0 || st1) {
+            uint32_t ha[8], hb[8];
+            bias_prelu_res_pack16_x2<kBf16>(ra, rb, e_bias + 48 + 16 * half, e_slope + 48 + 16 * half, x0[2 * half],
+                                            x0[2 * half + 1], x1[2 * half], x1[2 * half + 1], ha, hb);
+            if (st0) {
+              if (watch) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
+                for (int j = 0; j < 8; ++j) satm = sat_track(satm, ha[j]);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(out16 + pix0 * out_ctot + out_coff + 16 * half);
+              dst[0] = make_uint4(ha[0], ha[1], ha[2], ha[3]);
+              dst[1] = make_uint4(ha[4], ha[5], ha[6], ha[7]);
             }
-            uint4* dst = reinterpret_cast<uint4*>(out16 + pix0 * out_ctot + out_coff + 16 * half);
-            dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
-            dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
-          }
-          if (st1) {
-            bias_prelu_res_pack16<kBf16>(rb, s_bias + 48 + 16 * half, s_slope + 48 + 16 * half, x1[2 * half], x1[2 * half + 1], h);
-            if (watch) {
+            if (st1) {
+              if (watch) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) satm = sat_track(satm, h[j]);
+                for (int j = 0; j < 8; ++j) satm = sat_track(satm, hb[j]);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(out16 + pix1 * out_ctot + out_coff + 16 * half);
+              dst[0] = make_uint4(hb[0], hb[1], hb[2], hb[3]);
+              dst[1] = make_uint4(hb[4], hb[5], hb[6], hb[7]);
             }
-            uint4* dst = reinterpret_cast<uint4*>(out16 + pix1 * out_ctot + out_coff + 16 * half);
-            dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
-            dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
           }
         }
         dl.log(DBG_EV(2 + tx, it, 3, 2 * tx, 2));
@@ -517,11 +588,15 @@ int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_
     }
     woff += static_cast<uint64_t>(kdim[ps]) * ndim[ps] * 9 * 2;
   }
-  static const void* const kernels[4] = {reinterpret_cast<const void*>(dense_block_kernel<false, false>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<true, false>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<false, true>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<true, true>)};
-  if (int rc = ensure_max_dyn_smem(g_dense_opt_in, kernels, 4, DSMEM_BYTES, "cudaFuncSetAttribute(dense_block_kernel, smem)"))
+  static const void* const kernels[8] = {reinterpret_cast<const void*>(dense_block_kernel<false, false, false>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<true, false, false>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<false, true, false>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<true, true, false>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<false, false, true>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<true, false, true>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<false, true, true>),
+                                         reinterpret_cast<const void*>(dense_block_kernel<true, true, true>)};
+  if (int rc = ensure_max_dyn_smem(g_dense_opt_in, kernels, 8, DSMEM_BYTES, "cudaFuncSetAttribute(dense_block_kernel, smem)"))
     return rc;
   int sms = device_sm_count();
   if (sms <= 0) return B200DN_E_CUDA;
@@ -529,6 +604,7 @@ int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
   cfg->kind = 1;
   cfg->kernel = kernels[f.fmt + (f.dbg != nullptr ? 2 : 0)];
+  cfg->alt_kernel = kernels[f.fmt + (f.dbg != nullptr ? 2 : 0) + 4];      // the variant that reads cbias / cslope
   cfg->grid = grid;
   cfg->threads = DTHREADS;
   cfg->smem = DSMEM_BYTES;

@@ -582,6 +582,11 @@ struct __align__(64) FusedParams {
   void* out;
   int out_ctot, out_coff;
   int* sat_flag;
+  // bias / PReLU slopes by accumulator column [o0 | o1 | o2 | o3] as VALUES in the launch parameters (constant bank): the
+  // epilogue then reads them as instruction operands instead of broadcast LDS (11 % of the kernel's shared-memory
+  // wavefronts).  Filled by b200dn_dense_block_set_epilogue_constants; epi_const = 0: staged in shared memory from bias[] / slope[]
+  float cbias[80], cslope[80];
+  int epi_const;
   long long* dbg;                // optional timeline buffer (tools/dense_block_timeline.py): CTA 0 logs (event, clock64)
 #ifdef B200DN_TIMELINE
   unsigned long long* tl;        // diagnostics build only: the launch-timeline slots (TL_MARK)
@@ -612,6 +617,7 @@ struct LaunchCfg {
   const void* kernel;
   int grid, threads, smem, cluster;
   int cooperative;    // all CTAs must be co-resident (kind 2)
+  const void* alt_kernel;   // kind 1: the kernel variant that takes bias / slopes from the launch parameters
 };
 #ifdef B200DN_TIMELINE
 // 16 device slots for the next configured launch, labelled for the dump (igemm_sm100.cu)

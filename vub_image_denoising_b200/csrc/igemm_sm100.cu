@@ -887,6 +887,35 @@ extern "C" int b200dn_dense_block_prepare(const b200dn_dense_block_args* args, b
   return 0;
 }
 
+extern "C" int b200dn_dense_block_set_epilogue_constants(b200dn_igemm_prepared* prep, const float* const* bias_host,
+                                                         const float* const* slope_host) {
+  if (!prep || prep->cfg.kind != 1 || !prep->cfg.alt_kernel) {
+    b200dn::set_error("dense_block_set_epilogue_constants: not a prepared dense block");
+    return B200DN_E_ARG;
+  }
+  if (!bias_host || !slope_host) {
+    b200dn::set_error("dense_block_set_epilogue_constants: null argument");
+    return B200DN_E_ARG;
+  }
+  for (int j = 0; j < 4; ++j)
+    if (!bias_host[j] || !slope_host[j]) {
+      b200dn::set_error("dense_block_set_epilogue_constants: null bias / slope %d", j);
+      return B200DN_E_ARG;
+    }
+  b200dn::igemm::FusedParams& f = prep->cfg.f;
+  // accumulator-column order [o0 (16) | o1 (16) | o2 (16) | o3 (32)]
+  for (int c = 0; c < 80; ++c) {
+    const int j = c < 48 ? c >> 4 : 3, k = c < 48 ? c & 15 : c - 48;
+    f.cbias[c] = bias_host[j][k];
+    f.cslope[c] = slope_host[j][k];
+  }
+  if (!f.epi_const) {
+    f.epi_const = 1;
+    prep->cfg.kernel = prep->cfg.alt_kernel;
+  }
+  return 0;
+}
+
 extern "C" int64_t b200dn_conv_chain_workspace_bytes(const b200dn_igemm_args* layers, int n_layers) {
   if (!layers || n_layers < 1) {
     b200dn::set_error("conv_chain_workspace_bytes: bad arguments");

@@ -37,6 +37,8 @@ MODE_DENSE_BLOCK = 4     # layer_info "mode" of a fused block (the per-layer mod
 # they read instead of on a launch boundary (csrc/conv3x3_chain_sm100.cu); bit-equal to the four launches it replaces
 # B200DN_CHAIN: 0 = never, 1 = where a layer has at least two rounds of tiles per SM pair (default), 2 = wherever it applies
 _CHAIN_DENSE = int(os.environ.get("B200DN_CHAIN", "1"))
+# B200DN_DENSE_CONST=0: fused blocks stage bias / slopes in shared memory instead of taking them as launch parameters
+_DENSE_CONST = int(os.environ.get("B200DN_DENSE_CONST", "1"))
 MODE_CONV_CHAIN = 5      # layer_info "mode" of such a chain
 
 
@@ -498,9 +500,12 @@ class ForwardPlan:
         a.in_, a.in_ctot = src.hi.data_ptr(), src.ctot
         a.out, a.out_ctot, a.out_coff = dst.hi.data_ptr(), dst.ctot, dst_coff
         a.wfused = packed.data_ptr()
+        a._epi_dev = []
         for k in range(4):
             a.bias[k] = self._f32(convs[k].bias, self._keep)
+            a._epi_dev.append(self._keep[-1])
             a.slope[k] = self._f32(getattr(blk, f"actv_{k}").weight, self._keep)
+            a._epi_dev.append(self._keep[-1])
         if self.sat_flag is not None:
             a.sat_flag = self.sat_flag.data_ptr()
         g = C // 2
@@ -508,6 +513,20 @@ class ForwardPlan:
         self.flops += flops
         self.launches.append(a)
         self.layer_info.append(dict(mode=MODE_DENSE_BLOCK, H=H, W=W, cin=C, cout=C, flops=flops, nchw=False))
+
+    def _dense_constants(self, a: DenseBlockArgs, handle) -> None:
+        """Bias / PReLU slopes of a fused block as host values in the launch parameters (constant bank) instead of
+        shared-memory staging: the kernel sits at the shared-memory bandwidth wall (b200dn.h).  Needs one device -> host
+        read of 160 floats while the plan is built, so it is skipped when the plan is built inside a stream capture
+        (the kernel then stages the device arrays, same bits)."""
+        if not _DENSE_CONST or torch.cuda.is_current_stream_capturing():
+            return
+        host = [t.cpu() for t in a._epi_dev]                    # [b0, s0, b1, s1, ...] fp32 snapshots of this plan
+        fp = C.POINTER(C.c_float)
+        bias = (fp * 4)(*[C.cast(host[2 * k].data_ptr(), fp) for k in range(4)])
+        slope = (fp * 4)(*[C.cast(host[2 * k + 1].data_ptr(), fp) for k in range(4)])
+        _lib.check(self.lib.b200dn_dense_block_set_epilogue_constants(handle, bias, slope),
+                   "dense_block_set_epilogue_constants")
 
     def _dense(self, blk: _Params, src: _Act, dst: _Act, dst_coff: int, B, H, W, C) -> None:
         if self._fusable(C):
@@ -589,6 +608,7 @@ class ForwardPlan:
             if isinstance(a, DenseBlockArgs):
                 _lib.check(self.lib.b200dn_dense_block_prepare(C.byref(a), C.byref(h)),
                            f"dense_block_prepare (launch {len(handles)})")
+                self._dense_constants(a, h)
                 handles.append(h), launches.append(a), infos.append(info)
             elif isinstance(a, _Chain):
                 arr = (IgemmArgs * len(a.layers))(*a.layers)
