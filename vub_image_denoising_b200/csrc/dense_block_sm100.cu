@@ -107,7 +107,7 @@ struct DbgLog {
 // in TMEM belong to the pixel the next pass adds to; only the useful border shrinks per pass.
 template <int PS, bool kDbg>
 __device__ __forceinline__ void issue_pass(uint32_t sb, uint32_t bars, uint32_t tmem_base, uint32_t fmt, int ty, int it,
-                                           DbgLog<kDbg>& dl) {
+                                           int live_tx, DbgLog<kDbg>& dl) {
   constexpr uint32_t rowb = PS == 0 ? 64u : 32u;              // bytes per pixel row of A / per output row of B
   constexpr uint32_t layout = PS == 0 ? 4u : 6u;              // 64-byte / 32-byte swizzle
   constexpr uint32_t n_rows = PS == 0 ? 80u : PS == 1 ? 64u : PS == 2 ? 48u : 32u;
@@ -134,7 +134,13 @@ __device__ __forceinline__ void issue_pass(uint32_t sb, uint32_t bars, uint32_t 
     tc_fence_after();
     const int t = 2 * tx + ty;
     dl.log(DBG_EV(1, it, PS, t, 0));      // dependencies satisfied
-    if (elect_one()) {
+    // a tile column that lies entirely to the right of the image (the last region column of an image whose width is not a
+    // multiple of the region) produces only zeros: its MMAs are skipped, the commit still completes the tile's barrier
+    // and the epilogue stores the zeros the neighbouring tiles read as padding.  live_tx depends on the region only, so
+    // the branch is warp-uniform for the compiler too (the UMMA operands stay on the uniform datapath)
+    if (tx >= live_tx) {
+      if (elect_one()) umma_commit(bars + DB_TFULL + t * 8);
+    } else if (elect_one()) {
       const uint32_t d = tmem_base + static_cast<uint32_t>(t * NACC + PS * 16);
       const uint32_t o_pix = static_cast<uint32_t>((16 * ty) * FP + 8 * tx);   // source pixel of tap (0,0)
       const uint64_t adesc0 = make_kmajor_desc(sb + a_off + o_pix * rowb, FP * rowb, layout);
@@ -342,12 +348,17 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
       mbar_wait(bars + DB_XFULL, static_cast<uint32_t>(it & 1));
       dl.log(DBG_EV(1, it, 0, 0, 9));
-      issue_pass<0, kDbg>(sb, bars, tmem_base, fmt, ty, it, dl);
+      // tile columns of this region with at least one pixel column inside the image (1..3)
+      const int rx = region % regions_x;
+      int live_tx = 3;
+      if (rx * RW - 4 + 1 + 8 >= p.W) live_tx = 1;
+      else if (rx * RW - 4 + 1 + 16 >= p.W) live_tx = 2;
+      issue_pass<0, kDbg>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
       if (elect_one()) umma_commit(bars + DB_XEMPTY);     // this row's reads of the X frame have retired
       __syncwarp();
-      issue_pass<1, kDbg>(sb, bars, tmem_base, fmt, ty, it, dl);
-      issue_pass<2, kDbg>(sb, bars, tmem_base, fmt, ty, it, dl);
-      issue_pass<3, kDbg>(sb, bars, tmem_base, fmt, ty, it, dl);
+      issue_pass<1, kDbg>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
+      issue_pass<2, kDbg>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
+      issue_pass<3, kDbg>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
     }
   } else if (warp < 12) {
     // ===================================================== epilogue: group = tile column tx, both tile rows together
