@@ -259,6 +259,33 @@ __device__ __forceinline__ void bias_prelu_res_pack16_x2(const uint32_t (&ra)[16
   }
 }
 
+// Work order: region index -> (image, region row, region column).  When the last region column is cheap (fewer than three
+// live tile columns: most of its MMAs are skipped) those regions are numbered LAST, so that with static round-robin
+// they land in the final, partial round: at 2 images of 256 x 256 (300 regions on 148 SMs) the longest CTA then runs
+// 2 full + 1 cheap region instead of 3 full ones.
+struct RegionOrder {
+  int regions_x, regions_y, n_full, cheap_last;
+  __device__ __forceinline__ void init(const FusedParams& p) {
+    regions_x = p.regions_x, regions_y = p.regions_y;
+    cheap_last = (regions_x > 1 && (regions_x - 1) * RW - 4 + 1 + 16 >= p.W) ? 1 : 0;
+    n_full = cheap_last ? p.B * regions_y * (regions_x - 1) : p.num_regions;
+  }
+  __device__ __forceinline__ void decode(int idx, int& b, int& ry, int& rx) const {
+    if (idx < n_full) {
+      const int fx = regions_x - cheap_last, per = fx * regions_y;
+      b = idx / per;
+      const int r = idx - b * per;
+      ry = r / fx;
+      rx = r - ry * fx;
+    } else {
+      const int j = idx - n_full;
+      b = j / regions_y;
+      ry = j - b * regions_y;
+      rx = regions_x - 1;
+    }
+  }
+};
+
 template <bool kBf16, bool kDbg, bool kConst>
 __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -310,7 +337,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
   griddep_launch_dependents();
 
   const int num_regions = p.num_regions, grid = gridDim.x;
-  const int regions_x = p.regions_x, per_img = p.regions_x * p.regions_y;
+  RegionOrder order;
+  order.init(p);
   const int H = p.H, W = p.W;
 
   if (warp == W_PRODUCER) {
@@ -326,8 +354,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     griddep_wait();   // activations of the previous kernel
     int it = 0;
     for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
-      const int b = region / per_img, r = region - b * per_img;
-      const int ry = r / regions_x, rx = r - ry * regions_x;
+      int b, ry, rx;
+      order.decode(region, b, ry, rx);
       if (it > 0) mbar_wait(bars + DB_XEMPTY, static_cast<uint32_t>((it - 1) & 1));
       if (elect_one()) {
         mbar_arrive_expect_tx(bars + DB_XFULL, X_BYTES);
@@ -349,7 +377,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
       mbar_wait(bars + DB_XFULL, static_cast<uint32_t>(it & 1));
       dl.log(DBG_EV(1, it, 0, 0, 9));
       // tile columns of this region with at least one pixel column inside the image (1..3)
-      const int rx = region % regions_x;
+      int b_unused, ry_unused, rx;
+      order.decode(region, b_unused, ry_unused, rx);
       int live_tx = 3;
       if (rx * RW - 4 + 1 + 8 >= p.W) live_tx = 1;
       else if (rx * RW - 4 + 1 + 16 >= p.W) live_tx = 2;
@@ -383,8 +412,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     griddep_wait();   // the residual is read from the previous kernel's output
     int it = 0;
     for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
-      const int b = region / per_img, r = region - b * per_img;
-      const int ry = r / regions_x, rx = r - ry * regions_x;
+      int b, ry, rx;
+      order.decode(region, b, ry, rx);
       const int gx = rx * RW - 4 + fx, gy_0 = ry * RH - 4 + fy0, gy_1 = gy_0 + 16;
       const bool col_in = gx >= 0 && gx < W;
       const bool img0 = col_in && gy_0 >= 0 && gy_0 < H, img1 = col_in && gy_1 >= 0 && gy_1 < H;
