@@ -105,7 +105,7 @@ struct DbgLog {
 // taps (x 2 k16 steps in pass 0) with compile-time descriptor offsets and commit to the tile's t_full barrier.
 // Every pass uses the SAME pixel <-> accumulator-row grid (frame pixels [1,33) x [1,25)): the partial sums a pass leaves
 // in TMEM belong to the pixel the next pass adds to; only the useful border shrinks per pass.
-template <int PS, bool kDbg>
+template <int PS, bool kDbg, bool kPair>
 __device__ __forceinline__ void issue_pass(uint32_t sb, uint32_t bars, uint32_t tmem_base, uint32_t fmt, int ty, int it,
                                            int live_tx, DbgLog<kDbg>& dl) {
   constexpr uint32_t rowb = PS == 0 ? 64u : 32u;              // bytes per pixel row of A / per output row of B
@@ -113,7 +113,8 @@ __device__ __forceinline__ void issue_pass(uint32_t sb, uint32_t bars, uint32_t 
   constexpr uint32_t n_rows = PS == 0 ? 80u : PS == 1 ? 64u : PS == 2 ? 48u : 32u;
   constexpr uint32_t a_off = PS == 0 ? OFF_X : PS == 1 ? OFF_O0 : PS == 2 ? OFF_O1 : OFF_O2;
   constexpr uint32_t w_off = PS == 0 ? OFF_W0 : PS == 1 ? OFF_W1 : PS == 2 ? OFF_W2 : OFF_W3;
-  const uint32_t idesc = make_idesc_f16(fmt, n_rows);
+  constexpr uint32_t b_rows = kPair ? n_rows / 2 : n_rows;   // CTA pair: each SM keeps half of every weight tile
+  const uint32_t idesc = kPair ? make_idesc_f16(fmt, n_rows, 256u) : make_idesc_f16(fmt, n_rows);
   // completion (it * 4 + PS - 1) of the column barriers; each completion is waited for ONCE per pass: once a tile of
   // this pass is issued its epilogue may complete the barrier's next phase, and a second wait on the old parity
   // would never return
@@ -139,7 +140,10 @@ __device__ __forceinline__ void issue_pass(uint32_t sb, uint32_t bars, uint32_t 
     // and the epilogue stores the zeros the neighbouring tiles read as padding.  live_tx depends on the region only, so
     // the branch is warp-uniform for the compiler too (the UMMA operands stay on the uniform datapath)
     if (tx >= live_tx) {
-      if (elect_one()) umma_commit(bars + DB_TFULL + t * 8);
+      if (elect_one()) {
+        if (kPair) umma_commit_2cta(bars + DB_TFULL + t * 8, 3);
+        else umma_commit(bars + DB_TFULL + t * 8);
+      }
     } else if (elect_one()) {
       const uint32_t d = tmem_base + static_cast<uint32_t>(t * NACC + PS * 16);
       const uint32_t o_pix = static_cast<uint32_t>((16 * ty) * FP + 8 * tx);   // source pixel of tap (0,0)
@@ -149,12 +153,18 @@ __device__ __forceinline__ void issue_pass(uint32_t sb, uint32_t bars, uint32_t 
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const uint64_t ad = adesc0 + static_cast<uint64_t>(((dy * FP + dx) * rowb) >> 4);
-          const uint64_t bd = bdesc0 + static_cast<uint64_t>(((dy * 3 + dx) * n_rows * rowb) >> 4);
-          umma_f16(d, ad, bd, idesc, (PS == 0 && dy == 0 && dx == 0) ? 0u : 1u);
-          if (PS == 0) umma_f16(d, ad + 2, bd + 2, idesc, 1u);   // second 16 channels of x
+          const uint64_t bd = bdesc0 + static_cast<uint64_t>(((dy * 3 + dx) * b_rows * rowb) >> 4);
+          if (kPair) {
+            umma_f16_2cta(d, ad, bd, idesc, (PS == 0 && dy == 0 && dx == 0) ? 0u : 1u);
+            if (PS == 0) umma_f16_2cta(d, ad + 2, bd + 2, idesc, 1u);
+          } else {
+            umma_f16(d, ad, bd, idesc, (PS == 0 && dy == 0 && dx == 0) ? 0u : 1u);
+            if (PS == 0) umma_f16(d, ad + 2, bd + 2, idesc, 1u);   // second 16 channels of x
+          }
         }
       }
-      umma_commit(bars + DB_TFULL + t * 8);
+      if (kPair) umma_commit_2cta(bars + DB_TFULL + t * 8, 3);
+      else umma_commit(bars + DB_TFULL + t * 8);
     }
     __syncwarp();
     dl.log(DBG_EV(1, it, PS, t, 1));      // issued + committed
@@ -286,7 +296,11 @@ struct RegionOrder {
   }
 };
 
-template <bool kBf16, bool kDbg, bool kConst>
+// kPair: the two CTAs of a cluster work on two regions in lockstep; every MMA is a cta_group::2 instruction (M = 256:
+// tile t of both regions), issued by the leader CTA.  Each SM keeps its own X / O frames and HALF of every weight tile
+// (the hardware shares the halves), so the weight operand costs half the shared-memory wavefronts per SM — the kernel
+// sits at the shared-memory bandwidth wall (ncu: L1 90 %), and weights were 32 % of its operand bytes.
+template <bool kBf16, bool kDbg, bool kConst, bool kPair>
 __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_constant__ FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = smem_u32(smem_raw);
@@ -301,6 +315,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
   const float* e_slope = kConst ? p.cslope : s_slope;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   if (threadIdx.x == 0) TL_MARK(p, TL_ENTRY);
 
   if (warp == W_PRODUCER && lane == 0) {
@@ -315,12 +331,18 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     mbar_init(bars + DB_XFULL, 1);
     mbar_init(bars + DB_XEMPTY, 2);              // one tcgen05.commit per issuer warp
     for (int t = 0; t < NTILE; ++t) mbar_init(bars + DB_TFULL + t * 8, 1);     // one tcgen05.commit per pass
-    for (int c = 0; c < 3; ++c) mbar_init(bars + DB_OCOL + c * 8, 4);          // one arrive per warp of the column's group
+    // one arrive per warp of the column's group (pair: the groups of BOTH CTAs arrive on the leader's barrier)
+    for (int c = 0; c < 3; ++c) mbar_init(bars + DB_OCOL + c * 8, kPair ? 8 : 4);
     mbar_fence_init();
   }
   if (warp == W_ALLOC) {
-    tmem_alloc_all(smem_u32(tmem_ptr_s));
-    tmem_relinquish();
+    if (kPair) {
+      tmem_alloc_2cta(smem_u32(tmem_ptr_s), 512u);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc_all(smem_u32(tmem_ptr_s));
+      tmem_relinquish();
+    }
   }
   // bias / slopes of the four convs in accumulator-column order (static data: no dependency on the previous kernel)
   if (!kConst && threadIdx.x < NACC) {
@@ -330,13 +352,19 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     s_slope[c] = __ldg(p.slope[j] + k);
   }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();     // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
   if (threadIdx.x == 0) TL_MARK(p, TL_SETUP);
   griddep_launch_dependents();
 
-  const int num_regions = p.num_regions, grid = gridDim.x;
+  // work items: one region per CTA; a pair takes regions 2 * item + rank (the odd CTA of a last, half-empty pair runs a
+  // phantom region: it loads image 0's frame, computes in lockstep and stores nothing)
+  const int num_regions = p.num_regions;
+  const int num_items = kPair ? (num_regions + 1) >> 1 : num_regions;
+  const int first = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int grid = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   RegionOrder order;
   order.init(p);
   const int H = p.H, W = p.W;
@@ -344,26 +372,42 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
   if (warp == W_PRODUCER) {
     // ===================================================== producer: resident weights once, one X frame per region
     if (elect_one()) {
-      mbar_arrive_expect_tx(bars + DB_W, W0_BYTES + W1_BYTES + W2_BYTES + W3_BYTES);
-      tma_load_3d(sb + OFF_W0, &p.tmW[0], bars + DB_W, 0, 0, 0);
-      tma_load_3d(sb + OFF_W1, &p.tmW[1], bars + DB_W, 0, 0, 0);
-      tma_load_3d(sb + OFF_W2, &p.tmW[2], bars + DB_W, 0, 0, 0);
-      tma_load_3d(sb + OFF_W3, &p.tmW[3], bars + DB_W, 0, 0, 0);
+      if (kPair) {
+        // rows [rank * N / 2, (rank + 1) * N / 2) of every [tap][N][K] tile; both CTAs' bytes credit the leader's barrier
+        const uint32_t wbar = mapa_shared(bars + DB_W, 0);
+        if (leader) mbar_arrive_expect_tx(bars + DB_W, W0_BYTES + W1_BYTES + W2_BYTES + W3_BYTES);
+        tma_load_3d_2sm(sb + OFF_W0, &p.tmW[0], wbar, 0, static_cast<int>(rank) * 40, 0);
+        tma_load_3d_2sm(sb + OFF_W1, &p.tmW[1], wbar, 0, static_cast<int>(rank) * 32, 0);
+        tma_load_3d_2sm(sb + OFF_W2, &p.tmW[2], wbar, 0, static_cast<int>(rank) * 24, 0);
+        tma_load_3d_2sm(sb + OFF_W3, &p.tmW[3], wbar, 0, static_cast<int>(rank) * 16, 0);
+      } else {
+        mbar_arrive_expect_tx(bars + DB_W, W0_BYTES + W1_BYTES + W2_BYTES + W3_BYTES);
+        tma_load_3d(sb + OFF_W0, &p.tmW[0], bars + DB_W, 0, 0, 0);
+        tma_load_3d(sb + OFF_W1, &p.tmW[1], bars + DB_W, 0, 0, 0);
+        tma_load_3d(sb + OFF_W2, &p.tmW[2], bars + DB_W, 0, 0, 0);
+        tma_load_3d(sb + OFF_W3, &p.tmW[3], bars + DB_W, 0, 0, 0);
+      }
     }
     __syncwarp();
     griddep_wait();   // activations of the previous kernel
     int it = 0;
-    for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
-      int b, ry, rx;
-      order.decode(region, b, ry, rx);
+    for (int item = first; item < num_items; item += grid, ++it) {
+      const int region = kPair ? 2 * item + static_cast<int>(rank) : item;
+      int b = 0, ry = 0, rx = 0;
+      if (region < num_regions) order.decode(region, b, ry, rx);
       if (it > 0) mbar_wait(bars + DB_XEMPTY, static_cast<uint32_t>((it - 1) & 1));
       if (elect_one()) {
-        mbar_arrive_expect_tx(bars + DB_XFULL, X_BYTES);
-        tma_load_4d(sb + OFF_X, &p.tmX, bars + DB_XFULL, 0, rx * RW - 4, ry * RH - 4, b);
+        if (kPair) {
+          if (leader) mbar_arrive_expect_tx(bars + DB_XFULL, 2 * X_BYTES);
+          tma_load_4d_2sm(sb + OFF_X, &p.tmX, mapa_shared(bars + DB_XFULL, 0), 0, rx * RW - 4, ry * RH - 4, b);
+        } else {
+          mbar_arrive_expect_tx(bars + DB_XFULL, X_BYTES);
+          tma_load_4d(sb + OFF_X, &p.tmX, bars + DB_XFULL, 0, rx * RW - 4, ry * RH - 4, b);
+        }
       }
       __syncwarp();
     }
-  } else if (warp == W_ISSUER0 || warp == W_ISSUER0 + 1) {
+  } else if ((warp == W_ISSUER0 || warp == W_ISSUER0 + 1) && leader) {
     // ===================================================== MMA issuers: one warp per tile row
     // (a single issuing thread needs ~100 clocks per UMMA for descriptor arithmetic on the uniform datapath — the
     // timeline of the first version showed the tensor pipe idle behind it; two issuers and compile-time tap offsets)
@@ -373,21 +417,28 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     dl.init(p.dbg, 1, ty == 0);
     mbar_wait(bars + DB_W, 0);
     int it = 0;
-    for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
+    for (int item = first; item < num_items; item += grid, ++it) {
       mbar_wait(bars + DB_XFULL, static_cast<uint32_t>(it & 1));
       dl.log(DBG_EV(1, it, 0, 0, 9));
-      // tile columns of this region with at least one pixel column inside the image (1..3)
-      int b_unused, ry_unused, rx;
-      order.decode(region, b_unused, ry_unused, rx);
-      int live_tx = 3;
-      if (rx * RW - 4 + 1 + 8 >= p.W) live_tx = 1;
-      else if (rx * RW - 4 + 1 + 16 >= p.W) live_tx = 2;
-      issue_pass<0, kDbg>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
-      if (elect_one()) umma_commit(bars + DB_XEMPTY);     // this row's reads of the X frame have retired
+      // tile columns with at least one pixel column inside the image (1..3; the wider of the pair's two regions)
+      int live_tx = 1;
+      for (int r = 0; r < (kPair ? 2 : 1); ++r) {
+        const int region = kPair ? 2 * item + r : item;
+        if (region >= num_regions) continue;
+        int b_unused, ry_unused, rx;
+        order.decode(region, b_unused, ry_unused, rx);
+        const int l = (rx * RW - 4 + 1 + 8 >= p.W) ? 1 : (rx * RW - 4 + 1 + 16 >= p.W) ? 2 : 3;
+        live_tx = l > live_tx ? l : live_tx;
+      }
+      issue_pass<0, kDbg, kPair>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
+      if (elect_one()) {     // this row's reads of the X frame have retired
+        if (kPair) umma_commit_2cta(bars + DB_XEMPTY, 3);
+        else umma_commit(bars + DB_XEMPTY);
+      }
       __syncwarp();
-      issue_pass<1, kDbg>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
-      issue_pass<2, kDbg>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
-      issue_pass<3, kDbg>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
+      issue_pass<1, kDbg, kPair>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
+      issue_pass<2, kDbg, kPair>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
+      issue_pass<3, kDbg, kPair>(sb, bars, tmem_base, fmt, ty, it, live_tx, dl);
     }
   } else if (warp < 12) {
     // ===================================================== epilogue: group = tile column tx, both tile rows together
@@ -411,11 +462,15 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     dl.init(p.dbg, 2 + tx, we == 0 && tx < 2);
     griddep_wait();   // the residual is read from the previous kernel's output
     int it = 0;
-    for (int region = blockIdx.x; region < num_regions; region += grid, ++it) {
-      int b, ry, rx;
-      order.decode(region, b, ry, rx);
+    // pair: the column barriers the leader's issuers wait on collect the arrivals of both CTAs
+    const uint32_t ocol_bar = kPair ? mapa_shared(bars + DB_OCOL + tx * 8, 0) : bars + DB_OCOL + tx * 8;
+    for (int item = first; item < num_items; item += grid, ++it) {
+      const int region = kPair ? 2 * item + static_cast<int>(rank) : item;
+      int b = 0, ry = 0, rx = 0;
+      const bool live = region < num_regions;
+      if (live) order.decode(region, b, ry, rx);
       const int gx = rx * RW - 4 + fx, gy_0 = ry * RH - 4 + fy0, gy_1 = gy_0 + 16;
-      const bool col_in = gx >= 0 && gx < W;
+      const bool col_in = live && gx >= 0 && gx < W;
       const bool img0 = col_in && gy_0 >= 0 && gy_0 < H, img1 = col_in && gy_1 >= 0 && gy_1 < H;
       auto pass_epilogue = [&](const int ps) {
         // ---- o_ps of both tiles: bias + PReLU -> 16-bit -> shared memory (32-byte swizzled rows), zeros outside the image
@@ -456,7 +511,11 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
         fence_proxy_async_smem();     // generic-proxy stores -> visible to the UMMAs of the next pass
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bars + DB_OCOL + tx * 8);
+        if (lane == 0) {
+          // pair: the MMAs that read these stores run on this SM but are issued by the leader CTA's thread
+          if (kPair) mbar_arrive_remote(ocol_bar);
+          else mbar_arrive(ocol_bar);
+        }
         dl.log(DBG_EV(2 + tx, it, ps, 2 * tx, 2));     // o_ps written + arrived
       };
       if (kConst) {      // unrolled: the bias / slope indices are compile-time, i.e. c[0x0][...] operands of the FADD / FMUL
@@ -497,7 +556,10 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
           if (half == 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + DB_OCOL + tx * 8);      // TMEM columns of both tiles are free again
+            if (lane == 0) {      // TMEM columns of both tiles are free again (orders TMEM reads only: relaxed)
+              if (kPair) mbar_arrive_cluster(ocol_bar);
+              else mbar_arrive(ocol_bar);
+            }
             dl.log(DBG_EV(2 + tx, it, 3, 2 * tx, 1));
           }
           if (st0 || st1) {
@@ -530,11 +592,15 @@ __global__ void __launch_bounds__(DTHREADS, 1) dense_block_kernel(const __grid_c
     if (!kBf16) sat_report(p.sat_flag, satm);
   }
 
+  // pair: neither CTA may leave (or free its TMEM) while the other can still read its shared memory through an MMA or
+  // signal one of its barriers
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();
+  else __syncthreads();
   if (warp == W_ALLOC) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512u);
+    if (kPair) tmem_dealloc_2cta(tmem_base, 512u);
+    else tmem_dealloc(tmem_base, 512u);
   }
   if (threadIdx.x == 0) TL_MARK(p, TL_EXIT);
 }
@@ -564,6 +630,15 @@ __global__ void pack_dense_block_kernel(const float* __restrict__ w0, const floa
 }
 
 SmemOptIn g_dense_opt_in;
+
+// B200DN_DENSE_PAIR=0: one CTA per region (cta_group::1) instead of CTA pairs
+bool dense_pair_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("B200DN_DENSE_PAIR");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return v;
+}
 
 }  // namespace
 
@@ -612,13 +687,17 @@ int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_
       return B200DN_E_CUDA;
     }
   }
+  int sms = device_sm_count();
+  if (sms <= 0) return B200DN_E_CUDA;
+  // CTA pairs whenever there are at least two regions and no timeline buffer (the diagnostics stay on the one-CTA kernel)
+  const bool pair = dense_pair_enabled() && f.num_regions >= 2 && f.dbg == nullptr && sms >= 2 && a.max_ctas != 1;
   const uint8_t* wb = static_cast<const uint8_t*>(a.wfused);
   const uint32_t kdim[4] = {32, 16, 16, 16}, ndim[4] = {80, 64, 48, 32};
   uint64_t woff = 0;
   for (int ps = 0; ps < 4; ++ps) {
     uint64_t dims[3] = {kdim[ps], ndim[ps], 9};
     uint64_t str[2] = {kdim[ps] * 2ull, static_cast<uint64_t>(kdim[ps]) * ndim[ps] * 2ull};
-    uint32_t box[3] = {kdim[ps], ndim[ps], 9};
+    uint32_t box[3] = {kdim[ps], pair ? ndim[ps] / 2 : ndim[ps], 9};     // pair: each CTA loads half of the N rows
     CUresult r = encode_fn(&f.tmW[ps], dt, 3, const_cast<uint8_t*>(wb + woff), dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            ps == 0 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -628,26 +707,39 @@ int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_
     }
     woff += static_cast<uint64_t>(kdim[ps]) * ndim[ps] * 9 * 2;
   }
-  static const void* const kernels[8] = {reinterpret_cast<const void*>(dense_block_kernel<false, false, false>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<true, false, false>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<false, true, false>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<true, true, false>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<false, false, true>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<true, false, true>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<false, true, true>),
-                                         reinterpret_cast<const void*>(dense_block_kernel<true, true, true>)};
-  if (int rc = ensure_max_dyn_smem(g_dense_opt_in, kernels, 8, DSMEM_BYTES, "cudaFuncSetAttribute(dense_block_kernel, smem)"))
+  static const void* const kernels[12] = {reinterpret_cast<const void*>(dense_block_kernel<false, false, false, false>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<true, false, false, false>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<false, true, false, false>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<true, true, false, false>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<false, false, true, false>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<true, false, true, false>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<false, true, true, false>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<true, true, true, false>),
+                                          // CTA pairs (no timeline variant): [const][bf16]
+                                          reinterpret_cast<const void*>(dense_block_kernel<false, false, false, true>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<true, false, false, true>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<false, false, true, true>),
+                                          reinterpret_cast<const void*>(dense_block_kernel<true, false, true, true>)};
+  if (int rc = ensure_max_dyn_smem(g_dense_opt_in, kernels, 12, DSMEM_BYTES, "cudaFuncSetAttribute(dense_block_kernel, smem)"))
     return rc;
-  int sms = device_sm_count();
-  if (sms <= 0) return B200DN_E_CUDA;
+  cfg->kind = 1;
+  cfg->threads = DTHREADS;
+  cfg->smem = DSMEM_BYTES;
+  if (pair) {
+    int clusters = (f.num_regions + 1) / 2;
+    if (clusters > sms / 2) clusters = sms / 2;
+    if (a.max_ctas > 0 && 2 * clusters > a.max_ctas) clusters = a.max_ctas / 2;
+    cfg->kernel = kernels[8 + f.fmt];
+    cfg->alt_kernel = kernels[10 + f.fmt];      // the variant that reads cbias / cslope
+    cfg->grid = 2 * clusters;
+    cfg->cluster = 2;
+    return 0;
+  }
   int grid = f.num_regions < sms ? f.num_regions : sms;
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
-  cfg->kind = 1;
   cfg->kernel = kernels[f.fmt + (f.dbg != nullptr ? 2 : 0)];
   cfg->alt_kernel = kernels[f.fmt + (f.dbg != nullptr ? 2 : 0) + 4];      // the variant that reads cbias / cslope
   cfg->grid = grid;
-  cfg->threads = DTHREADS;
-  cfg->smem = DSMEM_BYTES;
   cfg->cluster = 1;
   return 0;
 }
