@@ -176,6 +176,16 @@ DIFF_FLOP_PER_SAMPLE = 40 * 96.30e9
 DIFF_BYTES_PER_SAMPLE = 40 * 425e6
 
 
+def _sampler_traffic_per_sample():
+    """DRAM bytes per diffusion sample from the committed ncu launch list of one sampler timestep (None if absent)."""
+    summ = ROOT / "profiles" / "r02_sampler_step_launches_summary.json"
+    if not summ.exists():
+        return None
+    d = json.loads(summ.read_text())
+    step_bytes = sum((k["dram_read_MB"] + k["dram_write_MB"]) * 1e6 for k in d["by_kernel"].values())
+    return step_bytes * DIFF_T / 16
+
+
 def _time_sampler(dm, noisy, reps, barrier):
     import torch.distributed as dist
     for _ in range(3):
@@ -227,7 +237,9 @@ def diffusion_metrics(b2, dev, world, rank, clean_dev, peaks, barrier):
                        "hbm_ms_per_sample": t_hbm * 1e3, "hbm_gbs_achieved": DIFF_BYTES_PER_SAMPLE / t_s / 1e9,
                        "algorithmic_flops_per_sample": DIFF_FLOP_PER_SAMPLE,
                        "algorithmic_bytes_per_sample": DIFF_BYTES_PER_SAMPLE, "peak_source": peaks["source"],
-                       "traffic": None, "kernels": "40 x (conv_in + 68 tcgen05 convolutions, level 0 as fused blocks, levels 1-2 as chained "
+                       "traffic": _sampler_traffic_per_sample(), "traffic_note": "dram__bytes_read+write of ONE sampler timestep at "
+                       "B = 16 (ncu launch list, profiles/r02_sampler_step_launches_summary.json) x 20 timesteps / 16 samples",
+                       "kernels": "40 x (conv_in + 68 tcgen05 convolutions, level 0 as fused blocks, levels 1-2 as chained "
                                                    "launches) + 20 x sampler_step per sample batch, "
                                                    "one CUDA graph; per-layer ncu captures under profiles/"}
     # (2) end to end through the public call with HOST buffers: pinned noisy batch -> H2D -> improved_sampling -> D2H

@@ -331,6 +331,27 @@ def test_fused_dense_block(shape, prec, built_lib):
         _lib.check(L.b200dn_dense_block_prepare(C.byref(a), C.byref(h)), "dense_block_prepare")
 
 
+@pytest.mark.parametrize("B,H,W,prec", [(2, 64, 64, "fp16"), (3, 40, 72, "bf16"), (1, 136, 56, "fp16"), (2, 256, 256, "fp16")])
+def test_fused_dense_block_cta_pairs_bit_equal(built_lib, monkeypatch, B, H, W, prec):
+    """B200DN_DENSE_PAIR=1 (opt-in): two regions per CTA pair, cta_group::2 MMAs, half of every weight tile per SM.  Same
+    tiles, same MMA order per accumulator row -> the network output is bit-identical to one CTA per region; odd region
+    counts exercise the phantom region of the last pair."""
+    import vub_image_denoising_b200 as b2
+    torch.manual_seed(3)
+    net = b2.RDUNet(base_filters=32).to(DEV).eval()
+    net.precision = prec
+    x = torch.rand(B, 3, H, W, device=DEV) * 2 - 1
+    with torch.no_grad():
+        monkeypatch.setenv("B200DN_DENSE_PAIR", "1")
+        net.invalidate_plans()
+        paired = [net(x).clone() for _ in range(3)]           # eager, graph capture, replay
+        monkeypatch.setenv("B200DN_DENSE_PAIR", "0")
+        net.invalidate_plans()
+        single = net(x)
+    for y in paired:
+        assert torch.equal(y, single)
+
+
 def test_fused_and_per_layer_networks_agree(built_lib, monkeypatch):
     """RDUNet_T(32) with the level-0 blocks fused vs launched layer by layer: same 16-bit rounding points, different
     fp32 summation order -> the two forwards agree to a few 16-bit ulps of the activations."""

@@ -3,6 +3,8 @@
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
         -c 600 --csv --log-file gpurun_out/bench_launches.csv python bench.py --steps 2 --warmup 1 --skip-diffusion --skip-cpu
     python tools/summarize_launches.py gpurun_out/bench_launches.csv profiles/r01_bench_launches
+    python tools/summarize_launches.py gpurun_out/sampler_step_ncu.csv profiles/r02_sampler_step_launches sampler
+        (launch list of `tools/forward_once.py sampler 32 16 fp16`: the last complete sampler timestep)
 
 Writes <out>.csv (one bench step, one line per launch, with a share-by-kernel header) and <out>_summary.json
 (`tensor_core_kernels.dram_bytes_per_launch` is what bench.py reports as roofline.traffic).  Per-launch times under
@@ -43,14 +45,22 @@ def main() -> None:
         elif m == "dram__bytes_write.sum":
             d["wr"] = v
     seq = list(launches.values())
-    # one bench step = from a gauss_noise launch up to (not including) the next one.  Steps of the e2e leg may carry
-    # a second forward (CUDA-graph warm-up), so take the first complete step with the smallest launch count.
-    starts = [i for i, d in enumerate(seq) if "gauss_noise" in d["kernel"]]
-    if len(starts) < 2:
-        raise SystemExit("need at least two bench steps in the capture")
-    segs = [seq[a:b] for a, b in zip(starts[:-1], starts[1:])]
-    fewest = min(len(g) for g in segs)
-    step = next(g for g in segs if len(g) == fewest)
+    sampler = len(sys.argv) > 3 and sys.argv[3] == "sampler"
+    if sampler:
+        # one sampler timestep = the launches after a sampler_step_kernel up to and including the next one
+        ends = [i for i, d in enumerate(seq) if "sampler_step" in d["kernel"]]
+        if len(ends) < 2:
+            raise SystemExit("need at least two sampler timesteps in the capture")
+        step = seq[ends[-2] + 1:ends[-1] + 1]
+    else:
+        # one bench step = from a gauss_noise launch up to (not including) the next one.  Steps of the e2e leg may carry
+        # a second forward (CUDA-graph warm-up), so take the first complete step with the smallest launch count.
+        starts = [i for i, d in enumerate(seq) if "gauss_noise" in d["kernel"]]
+        if len(starts) < 2:
+            raise SystemExit("need at least two bench steps in the capture")
+        segs = [seq[a:b] for a, b in zip(starts[:-1], starts[1:])]
+        fewest = min(len(g) for g in segs)
+        step = next(g for g in segs if len(g) == fewest)
     total_us = sum(d.get("us", 0.0) for d in step)
     by = OrderedDict()
     for d in step:
@@ -63,8 +73,13 @@ def main() -> None:
     t_us = sum(d["us"] for d in tens)
     t_bytes = sum(d.get("rd", 0.0) + d.get("wr", 0.0) for d in tens)
     cmd = "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python bench.py --steps 2 --warmup 1 --skip-diffusion --skip-cpu"
+    what = "one bench step: RDUNet(128) bf16, B=64 x 256x256, noise + forward + PSNR/SSIM."
+    if sampler:
+        cmd = "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none python tools/forward_once.py sampler 32 16 fp16"
+        what = ("ONE sampler timestep of DiffusionModel(RDUNet_T(32), 20).improved_sampling at B = 16: one forward over 32 images "
+                "(ingest conv + the plan's tensor-core launches) + sampler_step.")
     with open(out + ".csv", "w") as f:
-        f.write(f"# {cmd}\n# one bench step: RDUNet(128) bf16, B=64 x 256x256, noise + forward + PSNR/SSIM.  Cold-cache, serialised, "
+        f.write(f"# {cmd}\n# {what}  Cold-cache, serialised, "
                 "burst clocks: compare SHARES.\n# share by kernel (us, %, launches, DRAM read MB, DRAM write MB):\n")
         for k, b in sorted(by.items(), key=lambda kv: -kv[1]["us"]):
             f.write(f"#   {k:58s} {b['us']:10.1f} us {100 * b['us'] / total_us:5.1f}%  n={b['launches']:3d}  rd {b['rd'] / 1e6:10.1f}  wr {b['wr'] / 1e6:10.1f}\n")
