@@ -644,14 +644,11 @@ __global__ void pack_dense_block_kernel(const float* __restrict__ w0, const floa
 
 SmemOptIn g_dense_opt_in;
 
-// B200DN_DENSE_PAIR=1: CTA pairs (cta_group::2, half of every weight tile per SM).  Opt-in: 6 % faster on the level-0
-// blocks (1.10 -> 1.03 ms at 32 images, bit-identical outputs), but Nsight Compute 2025.2 cannot profile the pair kernel —
-// the first profiled launch completes, the next launch of the process fails with LaunchFailed (not the watchdog, not a
-// launch-configuration limit: profiles/r02_experiments_late_round.txt) — and the cause is not understood, so one CTA per
-// region stays the default.  Read at every prepare, so a process (and the tests) can use both.
+// B200DN_DENSE_PAIR=0: one CTA per region (cta_group::1) instead of CTA pairs.  Read at every prepare, so a process (and
+// the tests) can use both.
 bool dense_pair_enabled() {
   const char* e = getenv("B200DN_DENSE_PAIR");
-  return e ? atoi(e) != 0 : false;
+  return e ? atoi(e) != 0 : true;
 }
 }  // namespace
 
@@ -736,6 +733,11 @@ int configure_dense_block(const b200dn_dense_block_args& a, LaunchCfg* cfg, PFN_
   if (int rc = ensure_max_dyn_smem(g_dense_opt_in, kernels, 12, DSMEM_BYTES, "cudaFuncSetAttribute(dense_block_kernel, smem)"))
     return rc;
   cfg->kind = 1;
+  // never cooperative.  (Until late in round 2 this field was left unset for dense blocks and the handle was allocated
+  // without value-initialisation, so the blocks were launched with whatever the heap held — in practice the cooperative
+  // attribute.  Harmless for one-CTA launches, but cooperative + cluster launches are what ncu 2025.2 cannot run: it was
+  // the reason the CTA-pair variant "could not be profiled".)
+  cfg->cooperative = 0;
   cfg->threads = DTHREADS;
   cfg->smem = DSMEM_BYTES;
   if (pair) {

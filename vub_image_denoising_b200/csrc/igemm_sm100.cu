@@ -848,7 +848,7 @@ extern "C" int b200dn_igemm_prepare(const b200dn_igemm_args* args, b200dn_igemm_
     return B200DN_E_ARG;
   }
   *out = nullptr;
-  b200dn_igemm_prepared* h = new (std::nothrow) b200dn_igemm_prepared;
+  b200dn_igemm_prepared* h = new (std::nothrow) b200dn_igemm_prepared();     // value-initialised: no field of the launch configuration is left indeterminate
   if (!h) {
     b200dn::set_error("igemm_prepare: out of host memory");
     return B200DN_E_ARG;
@@ -873,7 +873,7 @@ extern "C" int b200dn_dense_block_prepare(const b200dn_dense_block_args* args, b
     if (int rc = b200dn::require_sm100()) return rc;
     if (int rc = b200dn::igemm::get_tensor_map_encoder(&enc)) return rc;
   }
-  b200dn_igemm_prepared* h = new (std::nothrow) b200dn_igemm_prepared;
+  b200dn_igemm_prepared* h = new (std::nothrow) b200dn_igemm_prepared();     // value-initialised: no field of the launch configuration is left indeterminate
   if (!h) {
     b200dn::set_error("dense_block_prepare: out of host memory");
     return B200DN_E_ARG;
@@ -931,7 +931,7 @@ extern "C" int b200dn_conv_chain_prepare(const b200dn_igemm_args* layers, int n_
     return B200DN_E_ARG;
   }
   *out = nullptr;
-  b200dn_igemm_prepared* h = new (std::nothrow) b200dn_igemm_prepared;
+  b200dn_igemm_prepared* h = new (std::nothrow) b200dn_igemm_prepared();     // value-initialised: no field of the launch configuration is left indeterminate
   if (!h) {
     b200dn::set_error("conv_chain_prepare: out of host memory");
     return B200DN_E_ARG;
