@@ -179,18 +179,29 @@ constexpr uint32_t OFF_W = 0;                                  // [cout_pad][64 
 constexpr uint32_t OFF_A = MAX_COUT * 128;                     // STAGES x {hi, lo}
 constexpr uint32_t OFF_BAR = OFF_A + STAGES * 2 * A_PLANE_BYTES;
 constexpr uint32_t OFF_EPI = OFF_BAR + 128;                    // bias[256], slope[256]
-constexpr uint32_t SMEM = 1024 + OFF_EPI + 2 * MAX_COUT * 4;
+// twin mode: per border class (first / inner / last row x column) and output channel, the sum of the 16-bit-rounded
+// t-plane weights over the taps that fall inside the image
+constexpr uint32_t OFF_TS = OFF_EPI + 2 * MAX_COUT * 4;
+constexpr uint32_t SMEM = 1024 + OFF_TS + 9 * MAX_COUT * 4;
 constexpr uint32_t B_AFULL = 0, B_AEMPTY = 16, B_TFULL = 32, B_TEMPTY = 48, B_TMEMPTR = 64;
 constexpr int THREADS = 544;   // 17 warps: 0-3 / 9-12 epilogue groups (column halves), 4-7 / 13-16 gather groups, 8 issuer
 
-template <int CIMG, bool HAS_T, bool kBf16>
+// kTwin (the sampler's call: B = 2 * Bx network images read the SAME Bx input images and differ only in a per-image
+// timestep, diffusion_RDUnet.py:43-47): the conv is linear, so conv_1([x, t]) = W_rgb * x + t * S with S the sum of the t-plane
+// weights over the in-image taps — a function of the pixel's border class only.  The image part is gathered and multiplied
+// ONCE per input image (K = 27) and the epilogue writes both network images, prelu(acc + b + t_a S) and prelu(acc + b + t_b S):
+// half the gather, which is what paces this kernel.
+template <int CIMG, bool HAS_T, bool kBf16, bool kTwin>
 __global__ void __launch_bounds__(THREADS, 1) conv_in_tc_kernel(const float* __restrict__ x, int Bx, const float* __restrict__ t,
                                                                 int64_t t_sb, int64_t t_sh, int64_t t_sw, int B, int H, int W,
                                                                 int cout, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, const float* __restrict__ slope,
                                                                 uint16_t* __restrict__ out0, int out_ctot, int* sat_flag) {
+  static_assert(!kTwin || HAS_T, "twin mode is the timestep network's");
   constexpr int CIN = CIMG + (HAS_T ? 1 : 0);
-  constexpr int K = CIN * 9;
+  constexpr int KW = CIN * 9;                                  // row length of w
+  constexpr int K = (kTwin ? CIMG : CIN) * 9;                  // K of the MMA (twin: the t plane is added in the epilogue)
+  constexpr bool GATHER_T = HAS_T && !kTwin;
   constexpr int NK16 = (K + 15) / 16;                          // 2 (K = 9, 18, 27) or 3 (K = 36)
   constexpr int NCHUNK = NK16 * 2;                             // 16-byte chunks (8 k) written per row and plane
   extern __shared__ uint8_t smem_raw[];
@@ -228,8 +239,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_in_tc_kernel(const float* __r
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int k0 = chunk * 8 + 2 * q;
-      const float a = (n < cout && k0 < K) ? __ldg(w + n * K + k0) : 0.f;
-      const float c = (n < cout && k0 + 1 < K) ? __ldg(w + n * K + k0 + 1) : 0.f;
+      const float a = (n < cout && k0 < K) ? __ldg(w + n * KW + k0) : 0.f;
+      const float c = (n < cout && k0 + 1 < K) ? __ldg(w + n * KW + k0 + 1) : 0.f;
       v[q] = kBf16 ? pack_bf16x2(a, c) : pack_f16x2(a, c);
     }
     *reinterpret_cast<uint4*>(sg + OFF_W + n * 128 + ((chunk ^ (n & 7)) << 4)) = make_uint4(v[0], v[1], v[2], v[3]);
@@ -237,6 +248,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv_in_tc_kernel(const float* __r
   for (int i = threadIdx.x; i < block_n; i += THREADS) {
     epi_bias[i] = i < cout ? __ldg(bias + i) : 0.f;
     epi_slope[i] = i < cout ? __ldg(slope + i) : 1.f;
+  }
+  float* t_sum = reinterpret_cast<float*>(sg + OFF_TS);         // [class = 3 * ycls + xcls][MAX_COUT]
+  if (kTwin) {
+    for (int i = threadIdx.x; i < 9 * block_n; i += THREADS) {
+      const int cls = i / block_n, n = i - cls * block_n;
+      const int ycls = cls / 3, xcls = cls - ycls * 3;          // 0 first row / column, 1 inner, 2 last
+      float sum = 0.f;
+      if (n < cout) {
+        for (int ky = (ycls == 0 ? 1 : 0); ky < (ycls == 2 ? 2 : 3); ++ky)
+          for (int kx = (xcls == 0 ? 1 : 0); kx < (xcls == 2 ? 2 : 3); ++kx) {
+            const float wv = __ldg(w + n * KW + CIMG * 9 + ky * 3 + kx);
+            sum += kBf16 ? bf16_lo(pack_bf16x2(wv, 0.f)) : f16_lo(pack_f16x2(wv, 0.f));   // the 16-bit weight the MMA would use
+          }
+      }
+      t_sum[cls * MAX_COUT + n] = sum;
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -246,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_in_tc_kernel(const float* __r
   griddep_launch_dependents();
 
   const int tiles_x = (W + TW_ - 1) / TW_, tiles_y = (H + TH_ - 1) / TH_;
-  const int num_tiles = B * tiles_x * tiles_y, grid = gridDim.x;
+  const int num_tiles = (kTwin ? Bx : B) * tiles_x * tiles_y, grid = gridDim.x;     // twin: one tile per INPUT image tile
   const int64_t hw = static_cast<int64_t>(H) * W;
 
   if ((warp >= 4 && warp < 8) || warp >= 13) {
@@ -276,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_in_tc_kernel(const float* __r
           const int64_t sp = static_cast<int64_t>(yy) * W + xc;
 #pragma unroll
           for (int ci = 0; ci < CIMG; ++ci) v[ci * 9 + ky * 3 + kx] = in ? __ldg(xb + ci * hw + sp) : 0.f;
-          if (HAS_T) v[CIMG * 9 + ky * 3 + kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
+          if (GATHER_T) v[CIMG * 9 + ky * 3 + kx] = in ? __ldg(t + b * t_sb + yy * t_sh + xc * t_sw) : 0.f;
         }
       }
       mbar_wait(bars + B_AEMPTY + st * 8, ph ^ 1u);       // the MMAs that read this stage have retired
@@ -351,8 +378,49 @@ __global__ void __launch_bounds__(THREADS, 1) conv_in_tc_kernel(const float* __r
       mbar_wait(bars + B_TFULL + st * 8, ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(we * 32) << 16) + static_cast<uint32_t>(st * block_n + col0);
-      epilogue_subtile(ea, taddr, ncols, epi_bias + col0, epi_slope + col0, valid, b, y, xx, pix, pix, col0,
-                       bars + B_TEMPTY + st * 8, satm);
+      if (!kTwin) {
+        epilogue_subtile(ea, taddr, ncols, epi_bias + col0, epi_slope + col0, valid, b, y, xx, pix, pix, col0,
+                         bars + B_TEMPTY + st * 8, satm);
+        continue;
+      }
+      // twin: both network images of this input pixel from one accumulator
+      float tj[2] = {0.f, 0.f};
+      if (valid) tj[0] = __ldg(t + b * t_sb), tj[1] = __ldg(t + (b + Bx) * t_sb);
+      const int cls = (y == 0 ? 0 : y == H - 1 ? 2 : 1) * 3 + (xx == 0 ? 0 : xx == W - 1 ? 2 : 1);
+      const float* ts = t_sum + cls * MAX_COUT + col0;
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (c0 + 16 >= ncols) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bars + B_TEMPTY + st * 8);
+        }
+        if (!valid) continue;
+        float base[16], sv[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) base[q] = __uint_as_float(r[q]) + epi_bias[col0 + c0 + q], sv[q] = ts[c0 + q];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t h[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float a0 = base[2 * q] + tj[j] * sv[2 * q], a1 = base[2 * q + 1] + tj[j] * sv[2 * q + 1];
+            a0 = a0 > 0.f ? a0 : a0 * epi_slope[col0 + c0 + 2 * q];
+            a1 = a1 > 0.f ? a1 : a1 * epi_slope[col0 + c0 + 2 * q + 1];
+            h[q] = pack2<kBf16>(a0, a1);
+          }
+          if (!kBf16 && ea.sat_flag != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) satm = igemm::sat_track(satm, h[q]);
+          }
+          const int64_t pj = pix + static_cast<int64_t>(j) * Bx * hw;
+          uint4* dst = reinterpret_cast<uint4*>(out0 + pj * out_ctot + col0 + c0);
+          dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
+          if (col0 + c0 + 8 < cout) dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+      }
     }
     sat_report(ea.sat_flag, satm);
   }
@@ -364,22 +432,28 @@ __global__ void __launch_bounds__(THREADS, 1) conv_in_tc_kernel(const float* __r
   }
 }
 
-template <int CIMG, bool HAS_T>
+template <int CIMG, bool HAS_T, bool kTwin>
 int launch(int grid, cudaStream_t s, const float* x, int Bx, const float* t, int64_t t_sb, int64_t t_sh, int64_t t_sw, int B,
            int H, int W, int cout, const float* w, const float* bias, const float* slope, bool bf16, uint16_t* o0, int out_ctot,
            int* sat_flag) {
-  static const void* const kernels[2] = {reinterpret_cast<const void*>(conv_in_tc_kernel<CIMG, HAS_T, false>),
-                                         reinterpret_cast<const void*>(conv_in_tc_kernel<CIMG, HAS_T, true>)};
+  static const void* const kernels[2] = {reinterpret_cast<const void*>(conv_in_tc_kernel<CIMG, HAS_T, false, kTwin>),
+                                         reinterpret_cast<const void*>(conv_in_tc_kernel<CIMG, HAS_T, true, kTwin>)};
   static SmemOptIn opt_in;
   if (int rc = ensure_max_dyn_smem(opt_in, kernels, 2, SMEM, "cudaFuncSetAttribute(conv_in_tc_kernel, smem)")) return rc;
   if (bf16)
-    conv_in_tc_kernel<CIMG, HAS_T, true><<<grid, THREADS, SMEM, s>>>(x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, o0,
-                                                                      out_ctot, sat_flag);
+    conv_in_tc_kernel<CIMG, HAS_T, true, kTwin><<<grid, THREADS, SMEM, s>>>(x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias,
+                                                                             slope, o0, out_ctot, sat_flag);
   else
-    conv_in_tc_kernel<CIMG, HAS_T, false><<<grid, THREADS, SMEM, s>>>(x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, o0,
-                                                                       out_ctot, sat_flag);
+    conv_in_tc_kernel<CIMG, HAS_T, false, kTwin><<<grid, THREADS, SMEM, s>>>(x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias,
+                                                                              slope, o0, out_ctot, sat_flag);
   B200DN_CUDA(cudaGetLastError());
   return 0;
+}
+
+// B200DN_CONV_IN_TWIN=0: the sampler's 2B batch gathers every input image twice (once per timestep) as a general batch
+bool twin_enabled() {
+  const char* e = getenv("B200DN_CONV_IN_TWIN");
+  return e ? atoi(e) != 0 : true;
 }
 
 bool enabled() {
@@ -432,16 +506,23 @@ extern "C" int b200dn_conv_in(const float* x, int Bx, int img_channels, const fl
   const bool single = prec == B200DN_PREC_BF16 || prec == B200DN_PREC_FP16;
   if (single && ingest_tc::enabled() && cout % 8 == 0 && cout <= ingest_tc::MAX_COUT) {
     // tensor-core ingest (single-plane modes): persistent grid, one CTA per SM
-    const int tiles = B * cdiv(W, ingest_tc::TW_) * cdiv(H, ingest_tc::TH_);
+    // the sampler's call shape: two network images per input image, per-image scalar timesteps
+    const bool twin = t != nullptr && B == 2 * Bx && t_sh == 0 && t_sw == 0 && H >= 2 && W >= 2 && ingest_tc::twin_enabled();
+    const int tiles = (twin ? Bx : B) * cdiv(W, ingest_tc::TW_) * cdiv(H, ingest_tc::TH_);
     int sms = device_sm_count();
     if (sms <= 0) return B200DN_E_CUDA;
     const int g = tiles < sms ? tiles : sms;
     const bool bf = prec == B200DN_PREC_BF16;
+    if (twin) {
+      if (img_channels == 3)
+        return ingest_tc::launch<3, true, true>(g, s, x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag);
+      return ingest_tc::launch<1, true, true>(g, s, x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag);
+    }
     if (img_channels == 3)
-      return t ? ingest_tc::launch<3, true>(g, s, x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag)
-               : ingest_tc::launch<3, false>(g, s, x, Bx, nullptr, 0, 0, 0, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag);
-    return t ? ingest_tc::launch<1, true>(g, s, x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag)
-             : ingest_tc::launch<1, false>(g, s, x, Bx, nullptr, 0, 0, 0, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag);
+      return t ? ingest_tc::launch<3, true, false>(g, s, x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag)
+               : ingest_tc::launch<3, false, false>(g, s, x, Bx, nullptr, 0, 0, 0, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag);
+    return t ? ingest_tc::launch<1, true, false>(g, s, x, Bx, t, t_sb, t_sh, t_sw, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag)
+             : ingest_tc::launch<1, false, false>(g, s, x, Bx, nullptr, 0, 0, 0, B, H, W, cout, w, bias, slope, bf, o0, out_ctot, sat_flag);
   }
   if (img_channels == 3)
     return t ? launch_conv_in<3, true>(grid, block, smem, s, x, Bx, t, t_sb, t_sh, t_sw, H, W, cout, w, bias, slope, prec, o0, o1, out_ctot, sat_flag)
