@@ -398,17 +398,27 @@ __global__ void __launch_bounds__(THREADS, 1) conv_in_tc_kernel(const float* __r
           if (lane == 0) mbar_arrive(bars + B_TEMPTY + st * 8);
         }
         if (!valid) continue;
-        float base[16], sv[16];
+        // bias / slopes: broadcast 128-bit loads; S: one 128-bit load per lane and 4 columns (its border class's row)
+        float base[16], sv[16], sl[16];
+        const float4* b4 = reinterpret_cast<const float4*>(epi_bias + col0 + c0);
+        const float4* s4 = reinterpret_cast<const float4*>(epi_slope + col0 + c0);
+        const float4* t4 = reinterpret_cast<const float4*>(ts + c0);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) base[q] = __uint_as_float(r[q]) + epi_bias[col0 + c0 + q], sv[q] = ts[c0 + q];
+        for (int q = 0; q < 4; ++q) {
+          const float4 bb = b4[q], ss = s4[q], tt = t4[q];
+          base[4 * q] = __uint_as_float(r[4 * q]) + bb.x, base[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + bb.y;
+          base[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + bb.z, base[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + bb.w;
+          sl[4 * q] = ss.x, sl[4 * q + 1] = ss.y, sl[4 * q + 2] = ss.z, sl[4 * q + 3] = ss.w;
+          sv[4 * q] = tt.x, sv[4 * q + 1] = tt.y, sv[4 * q + 2] = tt.z, sv[4 * q + 3] = tt.w;
+        }
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           uint32_t h[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float a0 = base[2 * q] + tj[j] * sv[2 * q], a1 = base[2 * q + 1] + tj[j] * sv[2 * q + 1];
-            a0 = a0 > 0.f ? a0 : a0 * epi_slope[col0 + c0 + 2 * q];
-            a1 = a1 > 0.f ? a1 : a1 * epi_slope[col0 + c0 + 2 * q + 1];
+            a0 = a0 > 0.f ? a0 : a0 * sl[2 * q];
+            a1 = a1 > 0.f ? a1 : a1 * sl[2 * q + 1];
             h[q] = pack2<kBf16>(a0, a1);
           }
           if (!kBf16 && ea.sat_flag != nullptr) {
